@@ -1,0 +1,472 @@
+// metamorph_b200 — bf16 GEMM on 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM, operands
+// staged by TMA into 128B-swizzled shared memory), persistent + warp-specialised, fused epilogues.
+//
+// One kernel family serves every dense contraction on the hot path (SURVEY.md §2.1 K1,K3,K5,K6,K8,
+// K11,K13,K14,K15,K16 and their dgrad/wgrad):
+//     C[M,N] = A[M,K] * B[N,K]^T           (nn.Linear forward;   A K-major,  B K-major)
+//     C[M,N] = A[M,K] * B[K,N]             (dgrad  dX = dY * W;  A K-major,  B MN-major)
+//     C[M,N] = A[K,M]^T * B[K,N]           (wgrad  dW = dY^T X;  A MN-major, B MN-major)
+// "K-major" = the contraction index is the contiguous one in memory. MN-major operands are fed to
+// the tensor core directly through the UMMA shared-memory descriptor (no transpose pass).
+//
+// CTA layout (256 threads, 1 CTA/SM, grid = min(#tiles, #SMs), static persistent schedule):
+//   warp 0 lane 0 : TMA producer        (global -> smem ring, kStages deep, mbarrier tx-count)
+//   warp 1 lane 0 : MMA issuer          (tcgen05.mma 128 x BN x 16, commit -> frees smem stage)
+//   warp 2        : TMEM allocator      (2 accumulator stages x BN fp32 columns)
+//   warps 4..7    : epilogue            (tcgen05.ld 32x32b -> registers -> fused math -> global)
+// The accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of i+1.
+#include "common.cuh"
+#include <mutex>
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;       // 64 bf16 = 128 bytes = one swizzle-128B row
+constexpr int UMMA_K = 16;
+constexpr int kThreads = 256;
+constexpr int GROUP_M = 16;  // rasterisation group (tiles sharing B columns stay L2-resident)
+
+enum Epilogue : int {
+  EPI_STORE = 0,           // C = acc
+  EPI_BIAS = 1,            // C = acc + bias[n]
+  EPI_BIAS_GELU_ERF = 2,   // C = gelu_erf(acc + bias[n])        (mm_projector / vision_head)
+  EPI_BIAS_GELU_TANH = 3,  // C = gelu_tanh(acc + bias[n])       (SigLIP fc1)
+  EPI_RESID = 4,           // C = acc + R[m,n]                   (o_proj / down_proj + residual)
+  EPI_BIAS_RESID = 5,      // C = acc + bias[n] + R[m,n]         (SigLIP out_proj / fc2)
+  EPI_SWIGLU = 6,          // columns interleaved [16 gate | 16 up]: C[m, n/2] = silu(g) * u
+};
+
+struct EpiParams {
+  void* C;
+  long long ldc;
+  const bf16* bias;
+  const bf16* resid;
+  long long ldr;
+  bf16* aux;  // EPI_SWIGLU: optional raw (gate|up interleaved) copy [M, N]
+  long long ld_aux;
+  int epi;
+  int out_f32;     // 1: C is fp32, 0: bf16
+  int accumulate;  // 1: C += result (C read in its own dtype)
+  float alpha;     // result scale applied to acc before everything else
+};
+
+template <int BN>
+struct Cfg {
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = 2 * BN;  // two accumulator stages
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ uint64_t make_desc_base(bool mn_major) {
+  // Shared-memory matrix descriptor (tcgen05): start[0,14) | LBO[16,30) | SBO[32,46) |
+  // version=1 [46,48) | layout_type[61,64) (2 = SWIZZLE_128B). Offsets are in 16-byte units.
+  const uint64_t sbo = 1024 >> 4;                           // 8 rows x 128 B
+  const uint64_t lbo = mn_major ? ((BK * 128) >> 4) : 1;    // MN-major: next 64-element MN chunk
+  return (lbo << 16) | (sbo << 32) | (1ull << 46) | (2ull << 61);
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                    const __grid_constant__ CUtensorMap tmap_b, int M, int N, int K,
+                    EpiParams ep) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + C::kStages * C::kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * C::kStages + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<C::kTmemCols>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  auto tile_coords = [&](int t, int& m_blk, int& n_blk) {
+    const int per_group = GROUP_M * num_n;
+    const int g = t / per_group;
+    const int first_m = g * GROUP_M;
+    const int gsz = min(GROUP_M, num_m - first_m);
+    const int r = t - g * per_group;
+    m_blk = first_m + (r % gsz);
+    n_blk = r / gsz;
+  };
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    int s = 0;
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      int m_blk, n_blk;
+      tile_coords(t, m_blk, n_blk);
+      const int m0 = m_blk * BM, n0 = n_blk * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(empty_bar(s), phase ^ 1);
+        const uint32_t sa = smem_base + s * C::kStageBytes;
+        const uint32_t sb = sa + C::kABytes;
+        mbar_arrive_expect_tx(full_bar(s), C::kStageBytes);
+        const int k0 = kb * BK;
+        if constexpr (!A_MN) {
+          tma_load_2d(sa, &tmap_a, full_bar(s), k0, m0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BM / 64; ++j)
+            tma_load_2d(sa + j * (BK * 128), &tmap_a, full_bar(s), m0 + 64 * j, k0);
+        }
+        if constexpr (!B_MN) {
+          tma_load_2d(sb, &tmap_b, full_bar(s), k0, n0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j)
+            tma_load_2d(sb + j * (BK * 128), &tmap_b, full_bar(s), n0 + 64 * j, k0);
+        }
+        if (++s == C::kStages) { s = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer
+    // Instruction descriptor (kind::f16): D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
+    // a_major bit15, b_major bit16 (1 = MN-major), N>>3 at [17,23), M>>4 at [24,29).
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(A_MN) << 15) |
+                           (uint32_t(B_MN) << 16) | (uint32_t(BN >> 3) << 17) |
+                           (uint32_t(BM >> 4) << 24);
+    const uint64_t desc_a_base = make_desc_base(A_MN);
+    const uint64_t desc_b_base = make_desc_base(B_MN);
+    // bytes to advance the operand start address per UMMA_K (=16) step
+    constexpr uint32_t a_kstep = A_MN ? (UMMA_K * 128) : (UMMA_K * 2);
+    constexpr uint32_t b_kstep = B_MN ? (UMMA_K * 128) : (UMMA_K * 2);
+    int s = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full_bar(s), phase);
+        tcgen05_fence_after();
+        const uint32_t sa = smem_base + s * C::kStageBytes;
+        const uint32_t sb = sa + C::kABytes;
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          const uint64_t da = desc_a_base | uint64_t(((sa + k * a_kstep) & 0x3FFFFu) >> 4);
+          const uint64_t db = desc_b_base | uint64_t(((sb + k * b_kstep) & 0x3FFFFu) >> 4);
+          umma_bf16_ss(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(empty_bar(s));                          // smem stage reusable once MMAs retire
+        if (kb == num_kb - 1) umma_commit(tfull_bar(acc));  // accumulator ready for the epilogue
+        if (++s == C::kStages) { s = 0; phase ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue warps
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      int m_blk, n_blk;
+      tile_coords(t, m_blk, n_blk);
+      const int row = m_blk * BM + q * 32 + lane;
+      const int n0 = n_blk * BN;
+      const bool row_ok = row < M;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= N) break;  // warp-uniform
+        __syncwarp();          // reconverge before the .aligned TMEM load
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr + c * 32, r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * ep.alpha;
+        const bool full_chunk = (col0 + 32 <= N);
+
+        if (ep.epi == EPI_SWIGLU) {
+          // chunk = 16 gate columns followed by their 16 up columns
+          if (row_ok) {
+            if (ep.aux != nullptr) {
+              bf16* ap = ep.aux + (long long)row * ep.ld_aux + col0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                int4 o;
+                o.x = pack_bf16x2(v[j], v[j + 1]);
+                o.y = pack_bf16x2(v[j + 2], v[j + 3]);
+                o.z = pack_bf16x2(v[j + 4], v[j + 5]);
+                o.w = pack_bf16x2(v[j + 6], v[j + 7]);
+                *reinterpret_cast<int4*>(ap + j) = o;
+              }
+            }
+            float o16[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o16[j] = silu(v[j]) * v[16 + j];
+            bf16* cp = reinterpret_cast<bf16*>(ep.C) + (long long)row * ep.ldc + (col0 >> 1);
+#pragma unroll
+            for (int j = 0; j < 16; j += 8) {
+              int4 o;
+              o.x = pack_bf16x2(o16[j], o16[j + 1]);
+              o.y = pack_bf16x2(o16[j + 2], o16[j + 3]);
+              o.z = pack_bf16x2(o16[j + 4], o16[j + 5]);
+              o.w = pack_bf16x2(o16[j + 6], o16[j + 7]);
+              *reinterpret_cast<int4*>(cp + j) = o;
+            }
+          }
+          continue;
+        }
+
+        if (ep.epi == EPI_BIAS || ep.epi == EPI_BIAS_GELU_ERF || ep.epi == EPI_BIAS_GELU_TANH ||
+            ep.epi == EPI_BIAS_RESID) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (full_chunk || col0 + j < N) v[j] += __bfloat162float(__ldg(ep.bias + col0 + j));
+        }
+        if (ep.epi == EPI_BIAS_GELU_ERF) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        } else if (ep.epi == EPI_BIAS_GELU_TANH) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
+        }
+        if (!row_ok) continue;  // lanes past M only take part in the TMEM load
+        if (ep.epi == EPI_RESID || ep.epi == EPI_BIAS_RESID) {
+          const bf16* rp = ep.resid + (long long)row * ep.ldr + col0;
+          if (full_chunk) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              const int4 rr = *reinterpret_cast<const int4*>(rp + j);
+              float2 f;
+              f = unpack_bf16x2(rr.x); v[j] += f.x; v[j + 1] += f.y;
+              f = unpack_bf16x2(rr.y); v[j + 2] += f.x; v[j + 3] += f.y;
+              f = unpack_bf16x2(rr.z); v[j + 4] += f.x; v[j + 5] += f.y;
+              f = unpack_bf16x2(rr.w); v[j + 6] += f.x; v[j + 7] += f.y;
+            }
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < N) v[j] += __bfloat162float(rp[j]);
+          }
+        }
+        if (ep.out_f32) {
+          float* cp = reinterpret_cast<float*>(ep.C) + (long long)row * ep.ldc + col0;
+          if (full_chunk) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              if (ep.accumulate) {
+                const float4 old = *reinterpret_cast<const float4*>(cp + j);
+                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+              }
+              *reinterpret_cast<float4*>(cp + j) = o;
+            }
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < N) cp[j] = ep.accumulate ? cp[j] + v[j] : v[j];
+          }
+        } else {
+          bf16* cp = reinterpret_cast<bf16*>(ep.C) + (long long)row * ep.ldc + col0;
+          if (full_chunk) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (ep.accumulate) {
+                const int4 old = *reinterpret_cast<const int4*>(cp + j);
+                float2 f;
+                f = unpack_bf16x2(old.x); v[j] += f.x; v[j + 1] += f.y;
+                f = unpack_bf16x2(old.y); v[j + 2] += f.x; v[j + 3] += f.y;
+                f = unpack_bf16x2(old.z); v[j + 4] += f.x; v[j + 5] += f.y;
+                f = unpack_bf16x2(old.w); v[j + 6] += f.x; v[j + 7] += f.y;
+              }
+              int4 o;
+              o.x = pack_bf16x2(v[j], v[j + 1]);
+              o.y = pack_bf16x2(v[j + 2], v[j + 3]);
+              o.z = pack_bf16x2(v[j + 4], v[j + 5]);
+              o.w = pack_bf16x2(v[j + 6], v[j + 7]);
+              *reinterpret_cast<int4*>(cp + j) = o;
+            }
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < N) {
+                float x = v[j];
+                if (ep.accumulate) x += __bfloat162float(cp[j]);
+                cp[j] = __float2bfloat16(x);
+              }
+          }
+        }
+      }
+      // all TMEM reads of this accumulator stage are complete (tcgen05.wait::ld above)
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc<C::kTmemCols>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side: TMA descriptor encoding + launch
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+// 2-D bf16 tensor: inner (contiguous) extent `inner`, outer extent `outer`, row pitch `ld` elements.
+int make_tmap(CUtensorMap* tm, const void* base, long long inner, long long outer, long long ld,
+              int box_inner, int box_outer) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) {
+    mm_set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    return MM_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    mm_set_error("cuTensorMapEncodeTiled failed (%d): base=%p inner=%lld outer=%lld ld=%lld", (int)r,
+                 base, inner, outer, ld);
+    return MM_ERR_CUDA;
+  }
+  return MM_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EpiParams& ep,
+           cudaStream_t stream) {
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] {
+    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    Cfg<BN>::kSmemBytes);
+  });
+  MM_CHECK_CUDA(attr_err);
+  const int num_tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  const int grid = num_tiles < mm_num_sms() ? num_tiles : mm_num_sms();
+  kern<<<grid, kThreads, Cfg<BN>::kSmemBytes, stream>>>(ta, tb, M, N, K, ep);
+  MM_CHECK_LAUNCH();
+  return MM_OK;
+}
+
+}  // namespace
+
+// See include/metamorph_b200.h for the contract.
+MM_API int mm_gemm_bf16(const void* A, const void* B, void* C, const void* bias,
+                            const void* resid, void* aux, long long M, long long N, long long K,
+                            long long lda, long long ldb, long long ldc, long long ldr,
+                            long long ld_aux, int a_mn_major, int b_mn_major, int epilogue,
+                            int out_f32, int accumulate, float alpha, int force_bn,
+                            cudaStream_t stream) {
+  MM_CHECK_ARG(M > 0 && N > 0 && K > 0, "mm_gemm_bf16: empty problem M=%lld N=%lld K=%lld", M, N, K);
+  MM_CHECK_ARG(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "mm_gemm_bf16: dims too large");
+  MM_CHECK_ARG(epilogue >= EPI_STORE && epilogue <= EPI_SWIGLU, "mm_gemm_bf16: bad epilogue %d",
+               epilogue);
+  MM_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && ((uintptr_t)C & 15) == 0,
+               "mm_gemm_bf16: A/B/C must be 16-byte aligned");
+  MM_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0, "mm_gemm_bf16: lda/ldb must be multiples of 8 elements");
+  MM_CHECK_ARG(out_f32 ? (ldc % 4 == 0) : (ldc % 8 == 0), "mm_gemm_bf16: ldc alignment (ldc=%lld)", ldc);
+  const bool needs_bias = epilogue == EPI_BIAS || epilogue == EPI_BIAS_GELU_ERF ||
+                          epilogue == EPI_BIAS_GELU_TANH || epilogue == EPI_BIAS_RESID;
+  const bool needs_res = epilogue == EPI_RESID || epilogue == EPI_BIAS_RESID;
+  MM_CHECK_ARG(!needs_bias || bias != nullptr, "mm_gemm_bf16: epilogue %d needs bias", epilogue);
+  MM_CHECK_ARG(!needs_res || (resid != nullptr && ldr % 8 == 0 && ((uintptr_t)resid & 15) == 0),
+               "mm_gemm_bf16: epilogue %d needs 16B-aligned residual with ldr%%8==0", epilogue);
+  if (epilogue == EPI_SWIGLU) {
+    MM_CHECK_ARG(N % 32 == 0 && !out_f32 && !accumulate && !a_mn_major && !b_mn_major,
+                 "mm_gemm_bf16: SWIGLU epilogue needs N%%32==0, bf16 out, K-major operands");
+    MM_CHECK_ARG(aux == nullptr || (ld_aux % 8 == 0 && ((uintptr_t)aux & 15) == 0),
+                 "mm_gemm_bf16: SWIGLU aux alignment");
+  }
+  MM_CHECK_ARG(!(a_mn_major && !b_mn_major), "mm_gemm_bf16: (A MN-major, B K-major) not instantiated");
+
+  int bn = 256;
+  if (force_bn == 128 || force_bn == 256) {
+    bn = force_bn;
+  } else {
+    const long long tiles256 = ceil_div64(M, BM) * ceil_div64(N, 256);
+    if (tiles256 < mm_num_sms() || N <= 128) bn = 128;
+  }
+
+  CUtensorMap ta, tb;
+  int rc;
+  if (!a_mn_major) rc = make_tmap(&ta, A, K, M, lda, BK, BM);       // A[M,K], K contiguous
+  else             rc = make_tmap(&ta, A, M, K, lda, 64, BK);       // A stored [K,M], M contiguous
+  if (rc) return rc;
+  if (!b_mn_major) rc = make_tmap(&tb, B, K, N, ldb, BK, bn);       // B[N,K], K contiguous
+  else             rc = make_tmap(&tb, B, N, K, ldb, 64, BK);       // B stored [K,N], N contiguous
+  if (rc) return rc;
+
+  EpiParams ep;
+  ep.C = C; ep.ldc = ldc;
+  ep.bias = reinterpret_cast<const bf16*>(bias);
+  ep.resid = reinterpret_cast<const bf16*>(resid); ep.ldr = ldr;
+  ep.aux = reinterpret_cast<bf16*>(aux); ep.ld_aux = ld_aux;
+  ep.epi = epilogue; ep.out_f32 = out_f32; ep.accumulate = accumulate; ep.alpha = alpha;
+
+  const int m = (int)M, n = (int)N, k = (int)K;
+  if (bn == 256) {
+    if (!a_mn_major && !b_mn_major) return launch<256, false, false>(ta, tb, m, n, k, ep, stream);
+    if (!a_mn_major && b_mn_major) return launch<256, false, true>(ta, tb, m, n, k, ep, stream);
+    return launch<256, true, true>(ta, tb, m, n, k, ep, stream);
+  } else {
+    if (!a_mn_major && !b_mn_major) return launch<128, false, false>(ta, tb, m, n, k, ep, stream);
+    if (!a_mn_major && b_mn_major) return launch<128, false, true>(ta, tb, m, n, k, ep, stream);
+    return launch<128, true, true>(ta, tb, m, n, k, ep, stream);
+  }
+}

@@ -1,0 +1,305 @@
+// metamorph_b200 — RMSNorm (fwd/bwd), LayerNorm (fwd) and rotary embedding kernels.
+// HBM-bound: one pass over each tensor, 128-bit accesses, fp32 statistics via warp shuffles.
+//   RMSNorm   : HF LlamaRMSNorm (modeling_llama.py:53-67)   y = w * bf16(x * rsqrt(mean(x^2)+eps))
+//   LayerNorm : SigLIP pre-LN (modeling_siglip.py:348,357)  eps 1e-6, affine
+//   RoPE      : HF apply_rotary_pos_emb (modeling_llama.py:146-168), rotate-half convention
+#include "common.cuh"
+
+namespace {
+
+constexpr int kNormThreads = 256;
+constexpr int kMaxVec = 4;  // 8-element vectors per thread => H <= 8192
+
+// ---------------------------------------------------------------------------------- RMSNorm fwd
+__global__ void __launch_bounds__(kNormThreads)
+rmsnorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ y,
+                   int M, int H, float eps) {
+  __shared__ float red[32];
+  const int nvec = H >> 3;
+  for (int row = blockIdx.x; row < M; row += gridDim.x) {
+    const bf16* xr = x + (size_t)row * H;
+    float xv[kMaxVec][8];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+      const int v = threadIdx.x + i * kNormThreads;
+      if (v < nvec) {
+        const int4 raw = *reinterpret_cast<const int4*>(xr + v * 8);
+        const uint32_t u[4] = {(uint32_t)raw.x, (uint32_t)raw.y, (uint32_t)raw.z, (uint32_t)raw.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack_bf16x2(u[j]);
+          xv[i][2 * j] = f.x;
+          xv[i][2 * j + 1] = f.y;
+          ss += f.x * f.x + f.y * f.y;
+        }
+      }
+    }
+    ss = block_sum(ss, red);
+    const float rstd = rsqrtf(ss / (float)H + eps);
+    bf16* yr = y + (size_t)row * H;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+      const int v = threadIdx.x + i * kNormThreads;
+      if (v < nvec) {
+        const int4 wraw = *reinterpret_cast<const int4*>(w + v * 8);
+        const uint32_t wu[4] = {(uint32_t)wraw.x, (uint32_t)wraw.y, (uint32_t)wraw.z, (uint32_t)wraw.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 wf = unpack_bf16x2(wu[j]);
+          // reference rounds the normalised activation to bf16 before the weight multiply
+          const float n0 = __bfloat162float(__float2bfloat16(xv[i][2 * j] * rstd));
+          const float n1 = __bfloat162float(__float2bfloat16(xv[i][2 * j + 1] * rstd));
+          o[j] = pack_bf16x2(wf.x * n0, wf.y * n1);
+        }
+        *reinterpret_cast<int4*>(yr + v * 8) = make_int4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------- RMSNorm bwd
+// dx = dres_in + rstd * (dy*w - xhat * mean(dy*w*xhat));  dw += sum_rows dy * xhat  (fp32 atomics)
+__global__ void __launch_bounds__(kNormThreads)
+rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                   const bf16* __restrict__ w, const bf16* __restrict__ dres_in,
+                   bf16* __restrict__ dx, float* __restrict__ dw_accum, int M, int H, float eps) {
+  __shared__ float red[32];
+  const int nvec = H >> 3;
+  float dwp[kMaxVec][8];
+  float wv[kMaxVec][8];
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int v = threadIdx.x + i * kNormThreads;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      dwp[i][j] = 0.f;
+      wv[i][j] = (v < nvec) ? __bfloat162float(w[v * 8 + j]) : 0.f;
+    }
+  }
+  for (int row = blockIdx.x; row < M; row += gridDim.x) {
+    const bf16* xr = x + (size_t)row * H;
+    const bf16* dyr = dy + (size_t)row * H;
+    float xv[kMaxVec][8], gv[kMaxVec][8];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+      const int v = threadIdx.x + i * kNormThreads;
+      if (v < nvec) {
+        const int4 rx = *reinterpret_cast<const int4*>(xr + v * 8);
+        const int4 rg = *reinterpret_cast<const int4*>(dyr + v * 8);
+        const uint32_t ux[4] = {(uint32_t)rx.x, (uint32_t)rx.y, (uint32_t)rx.z, (uint32_t)rx.w};
+        const uint32_t ug[4] = {(uint32_t)rg.x, (uint32_t)rg.y, (uint32_t)rg.z, (uint32_t)rg.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack_bf16x2(ux[j]);
+          const float2 g = unpack_bf16x2(ug[j]);
+          xv[i][2 * j] = f.x; xv[i][2 * j + 1] = f.y;
+          gv[i][2 * j] = g.x; gv[i][2 * j + 1] = g.y;
+          ss += f.x * f.x + f.y * f.y;
+        }
+      }
+    }
+    ss = block_sum(ss, red);
+    const float rstd = rsqrtf(ss / (float)H + eps);
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+      const int v = threadIdx.x + i * kNormThreads;
+      if (v < nvec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xhat = xv[i][j] * rstd;
+          dwp[i][j] += gv[i][j] * xhat;
+          gv[i][j] *= wv[i][j];       // dxhat
+          dot += gv[i][j] * xhat;
+          xv[i][j] = xhat;
+        }
+      }
+    }
+    dot = block_sum(dot, red) / (float)H;
+    bf16* dxr = dx + (size_t)row * H;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+      const int v = threadIdx.x + i * kNormThreads;
+      if (v < nvec) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = rstd * (gv[i][j] - xv[i][j] * dot);
+        if (dres_in != nullptr) {
+          const int4 rr = *reinterpret_cast<const int4*>(dres_in + (size_t)row * H + v * 8);
+          const uint32_t ur[4] = {(uint32_t)rr.x, (uint32_t)rr.y, (uint32_t)rr.z, (uint32_t)rr.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = unpack_bf16x2(ur[j]);
+            o[2 * j] += f.x;
+            o[2 * j + 1] += f.y;
+          }
+        }
+        *reinterpret_cast<int4*>(dxr + v * 8) =
+            make_int4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
+                      pack_bf16x2(o[6], o[7]));
+      }
+    }
+  }
+  if (dw_accum != nullptr) {
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+      const int v = threadIdx.x + i * kNormThreads;
+      if (v < nvec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(dw_accum + v * 8 + j, dwp[i][j]);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------- LayerNorm fwd
+__global__ void __launch_bounds__(kNormThreads)
+layernorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
+                     const bf16* __restrict__ b, bf16* __restrict__ y, int M, int H, float eps) {
+  __shared__ float red[32];
+  const int nvec = H >> 3;
+  for (int row = blockIdx.x; row < M; row += gridDim.x) {
+    const bf16* xr = x + (size_t)row * H;
+    float xv[kMaxVec][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+      const int v = threadIdx.x + i * kNormThreads;
+      if (v < nvec) {
+        const int4 raw = *reinterpret_cast<const int4*>(xr + v * 8);
+        const uint32_t u[4] = {(uint32_t)raw.x, (uint32_t)raw.y, (uint32_t)raw.z, (uint32_t)raw.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack_bf16x2(u[j]);
+          xv[i][2 * j] = f.x; xv[i][2 * j + 1] = f.y;
+          s += f.x + f.y;
+        }
+      }
+    }
+    const float mean = block_sum(s, red) / (float)H;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+      const int v = threadIdx.x + i * kNormThreads;
+      if (v < nvec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = xv[i][j] - mean;
+          ss += d * d;
+        }
+      }
+    }
+    const float rstd = rsqrtf(block_sum(ss, red) / (float)H + eps);
+    bf16* yr = y + (size_t)row * H;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+      const int v = threadIdx.x + i * kNormThreads;
+      if (v < nvec) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          o[j] = (xv[i][j] - mean) * rstd * __bfloat162float(w[v * 8 + j]) +
+                 __bfloat162float(b[v * 8 + j]);
+        *reinterpret_cast<int4*>(yr + v * 8) =
+            make_int4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
+                      pack_bf16x2(o[6], o[7]));
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------- RoPE
+// In-place rotate-half on the first `n_rot_heads` heads of each row of a [M, ld] buffer.
+// cos/sin: fp32 tables [n_pos, d/2]; pos[M] int32. `sign` = +1 forward, -1 backward (transpose).
+__global__ void rope_kernel(bf16* __restrict__ qkv, const int* __restrict__ pos,
+                            const float* __restrict__ cos_t, const float* __restrict__ sin_t, int M,
+                            long long ld, int n_rot_heads, int d, float sign) {
+  const int half = d >> 1;
+  const int vec_per_head = half >> 3;
+  const long long total = (long long)M * n_rot_heads * vec_per_head;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(idx % vec_per_head);
+    const long long t = idx / vec_per_head;
+    const int head = (int)(t % n_rot_heads);
+    const int row = (int)(t / n_rot_heads);
+    bf16* p = qkv + (size_t)row * ld + head * d + v * 8;
+    const int4 lo = *reinterpret_cast<const int4*>(p);
+    const int4 hi = *reinterpret_cast<const int4*>(p + half);
+    const float* cp = cos_t + (size_t)pos[row] * half + v * 8;
+    const float* sp = sin_t + (size_t)pos[row] * half + v * 8;
+    const uint32_t ul[4] = {(uint32_t)lo.x, (uint32_t)lo.y, (uint32_t)lo.z, (uint32_t)lo.w};
+    const uint32_t uh[4] = {(uint32_t)hi.x, (uint32_t)hi.y, (uint32_t)hi.z, (uint32_t)hi.w};
+    uint32_t ol[4], oh[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 a = unpack_bf16x2(ul[j]);
+      const float2 b = unpack_bf16x2(uh[j]);
+      const float c0 = cp[2 * j], c1 = cp[2 * j + 1];
+      const float s0 = sign * sp[2 * j], s1 = sign * sp[2 * j + 1];
+      ol[j] = pack_bf16x2(a.x * c0 - b.x * s0, a.y * c1 - b.y * s1);
+      oh[j] = pack_bf16x2(b.x * c0 + a.x * s0, b.y * c1 + a.y * s1);
+    }
+    *reinterpret_cast<int4*>(p) = make_int4(ol[0], ol[1], ol[2], ol[3]);
+    *reinterpret_cast<int4*>(p + half) = make_int4(oh[0], oh[1], oh[2], oh[3]);
+  }
+}
+
+int norm_grid(int M) {
+  const int cap = mm_num_sms() * 8;
+  return M < cap ? M : cap;
+}
+
+}  // namespace
+
+MM_API int mm_rmsnorm_fwd(const void* x, const void* w, void* y, long long M, long long H, float eps,
+                          cudaStream_t stream) {
+  MM_CHECK_ARG(M > 0 && H > 0 && H % 8 == 0 && H <= 8 * kNormThreads * kMaxVec,
+               "mm_rmsnorm_fwd: need H%%8==0 and H<=%d (H=%lld)", 8 * kNormThreads * kMaxVec, H);
+  rmsnorm_fwd_kernel<<<norm_grid((int)M), kNormThreads, 0, stream>>>(
+      (const bf16*)x, (const bf16*)w, (bf16*)y, (int)M, (int)H, eps);
+  MM_CHECK_LAUNCH();
+  return MM_OK;
+}
+
+MM_API int mm_rmsnorm_bwd(const void* dy, const void* x, const void* w, const void* dres_in, void* dx,
+                          float* dw_accum, long long M, long long H, float eps, cudaStream_t stream) {
+  MM_CHECK_ARG(M > 0 && H > 0 && H % 8 == 0 && H <= 8 * kNormThreads * kMaxVec,
+               "mm_rmsnorm_bwd: need H%%8==0 and H<=%d (H=%lld)", 8 * kNormThreads * kMaxVec, H);
+  const int cap = mm_num_sms() * 4;
+  const int grid = M < cap ? (int)M : cap;
+  rmsnorm_bwd_kernel<<<grid, kNormThreads, 0, stream>>>((const bf16*)dy, (const bf16*)x,
+                                                        (const bf16*)w, (const bf16*)dres_in,
+                                                        (bf16*)dx, dw_accum, (int)M, (int)H, eps);
+  MM_CHECK_LAUNCH();
+  return MM_OK;
+}
+
+MM_API int mm_layernorm_fwd(const void* x, const void* w, const void* b, void* y, long long M,
+                            long long H, float eps, cudaStream_t stream) {
+  MM_CHECK_ARG(M > 0 && H > 0 && H % 8 == 0 && H <= 8 * kNormThreads * kMaxVec,
+               "mm_layernorm_fwd: need H%%8==0 and H<=%d (H=%lld)", 8 * kNormThreads * kMaxVec, H);
+  layernorm_fwd_kernel<<<norm_grid((int)M), kNormThreads, 0, stream>>>(
+      (const bf16*)x, (const bf16*)w, (const bf16*)b, (bf16*)y, (int)M, (int)H, eps);
+  MM_CHECK_LAUNCH();
+  return MM_OK;
+}
+
+MM_API int mm_rope_inplace(void* qkv, const int* pos, const float* cos_t, const float* sin_t,
+                           long long M, long long ld, int n_rot_heads, int head_dim, int backward,
+                           cudaStream_t stream) {
+  MM_CHECK_ARG(M > 0 && head_dim % 16 == 0 && ld % 8 == 0 && n_rot_heads > 0,
+               "mm_rope_inplace: need head_dim%%16==0, ld%%8==0");
+  const long long total = M * n_rot_heads * (head_dim / 16);
+  const int threads = 256;
+  long long blocks = ceil_div64(total, threads);
+  const long long cap = (long long)mm_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  rope_kernel<<<(int)blocks, threads, 0, stream>>>((bf16*)qkv, pos, cos_t, sin_t, (int)M, ld,
+                                                   n_rot_heads, head_dim, backward ? -1.f : 1.f);
+  MM_CHECK_LAUNCH();
+  return MM_OK;
+}
