@@ -47,3 +47,255 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
          c_int(1 if out_dtype == torch.float32 else 0), c_int(int(accumulate)), c_float(alpha),
          c_int(force_bn), stream_ptr())
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# norms / rope
+# ------------------------------------------------------------------------------------------------
+def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float, out: Optional[torch.Tensor] = None):
+    require_cuda(x, w)
+    assert x.dim() == 2 and x.is_contiguous() and x.dtype == torch.bfloat16
+    out = torch.empty_like(x) if out is None else out
+    call("mm_rmsnorm_fwd", ptr(x), ptr(w), ptr(out), ll(x.shape[0]), ll(x.shape[1]), c_float(eps),
+         stream_ptr())
+    return out
+
+
+def rmsnorm_bwd(dy, x, w, eps, dres_in=None, dw_accum=None, out=None):
+    """dx = dres_in + d(rmsnorm)/dx ; dw_accum (fp32 [H]) += sum_rows dy * xhat."""
+    require_cuda(dy, x, w)
+    assert dy.is_contiguous() and x.is_contiguous()
+    out = torch.empty_like(x) if out is None else out
+    call("mm_rmsnorm_bwd", ptr(dy), ptr(x), ptr(w), ptr(dres_in), ptr(out), ptr(dw_accum),
+         ll(x.shape[0]), ll(x.shape[1]), c_float(eps), stream_ptr())
+    return out
+
+
+def layernorm(x, w, b, eps, out=None):
+    require_cuda(x, w, b)
+    assert x.dim() == 2 and x.is_contiguous()
+    out = torch.empty_like(x) if out is None else out
+    call("mm_layernorm_fwd", ptr(x), ptr(w), ptr(b), ptr(out), ll(x.shape[0]), ll(x.shape[1]),
+         c_float(eps), stream_ptr())
+    return out
+
+
+def rope_(qkv: torch.Tensor, pos: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor,
+          n_rot_heads: int, head_dim: int, backward: bool = False):
+    """In-place rotary embedding on the first n_rot_heads heads of each row of qkv [M, ld]."""
+    require_cuda(qkv, pos, cos, sin)
+    assert pos.dtype == torch.int32 and cos.dtype == torch.float32 and cos.is_contiguous()
+    assert qkv.dim() == 2 and qkv.stride(1) == 1
+    call("mm_rope_inplace", ptr(qkv), ptr(pos), ptr(cos), ptr(sin), ll(qkv.shape[0]),
+         ll(qkv.stride(0)), c_int(n_rot_heads), c_int(head_dim), c_int(int(backward)), stream_ptr())
+    return qkv
+
+
+# ------------------------------------------------------------------------------------------------
+# elementwise
+# ------------------------------------------------------------------------------------------------
+def swiglu_bwd(gu, dact, dgu=None, act=None):
+    require_cuda(gu, dact)
+    M, I2 = gu.shape
+    I = I2 // 2
+    assert gu.is_contiguous() and dact.is_contiguous() and dact.shape == (M, I)
+    dgu = torch.empty_like(gu) if dgu is None else dgu
+    call("mm_swiglu_bwd", ptr(gu), ptr(dact), ptr(dgu), ptr(act), ll(M), ll(I), stream_ptr())
+    return dgu
+
+
+def gelu(z, out=None):
+    require_cuda(z)
+    assert z.is_contiguous()
+    out = torch.empty_like(z) if out is None else out
+    call("mm_gelu_fwd", ptr(z), ptr(out), ll(z.numel()), stream_ptr())
+    return out
+
+
+def gelu_bwd(z, da, out=None):
+    require_cuda(z, da)
+    assert z.is_contiguous() and da.is_contiguous()
+    out = torch.empty_like(z) if out is None else out
+    call("mm_gelu_bwd", ptr(z), ptr(da), ptr(out), ll(z.numel()), stream_ptr())
+    return out
+
+
+def colsum_accum(x, out_f32):
+    require_cuda(x, out_f32)
+    assert x.dim() == 2 and x.stride(1) == 1 and out_f32.dtype == torch.float32
+    call("mm_colsum_accum", ptr(x), ptr(out_f32), ll(x.shape[0]), ll(x.shape[1]), ll(x.stride(0)),
+         stream_ptr())
+    return out_f32
+
+
+def im2col_patch14(images: torch.Tensor, ldp: int = 640):
+    require_cuda(images)
+    n, c, s, s2 = images.shape
+    assert c == 3 and s == s2 and images.is_contiguous() and images.dtype == torch.bfloat16
+    g = s // 14
+    out = torch.empty((n * g * g, ldp), dtype=torch.bfloat16, device=images.device)
+    call("mm_im2col_patch14", ptr(images), ptr(out), c_int(n), c_int(s), c_int(ldp), stream_ptr())
+    return out
+
+
+def add_pos_emb_(x, pos):
+    require_cuda(x, pos)
+    assert x.is_contiguous() and pos.is_contiguous()
+    call("mm_add_pos_emb", ptr(x), ptr(pos), ll(x.shape[0]), c_int(pos.shape[0]), c_int(x.shape[1]),
+         stream_ptr())
+    return x
+
+
+def sumsq_accum(x, out_f32):
+    require_cuda(x, out_f32)
+    assert x.is_contiguous()
+    call("mm_sumsq_bf16_accum", ptr(x), ptr(out_f32), ll(x.numel()), stream_ptr())
+    return out_f32
+
+
+# ------------------------------------------------------------------------------------------------
+# interleave (K9) and row gathers
+# ------------------------------------------------------------------------------------------------
+def interleave_gather(embed_w, img_feats, row_map, out=None):
+    require_cuda(embed_w, img_feats, row_map)
+    assert row_map.dtype == torch.int32 and embed_w.is_contiguous()
+    H = embed_w.shape[1]
+    R = row_map.numel()
+    out = torch.empty((R, H), dtype=torch.bfloat16, device=embed_w.device) if out is None else out
+    call("mm_interleave_gather", ptr(embed_w), ptr(img_feats), ptr(row_map), ptr(out), ll(R), c_int(H),
+         stream_ptr())
+    return out
+
+
+def interleave_scatter(dout, row_map, dembed, dimg):
+    require_cuda(dout, row_map, dembed, dimg)
+    assert dout.is_contiguous()
+    call("mm_interleave_scatter", ptr(dout), ptr(row_map), ptr(dembed), ptr(dimg), ll(dout.shape[0]),
+         c_int(dout.shape[1]), stream_ptr())
+
+
+def gather_rows(x, idx, out=None):
+    require_cuda(x, idx)
+    assert idx.dtype == torch.int32 and x.is_contiguous()
+    out = torch.empty((idx.numel(), x.shape[1]), dtype=x.dtype, device=x.device) if out is None else out
+    if idx.numel() > 0:
+        call("mm_gather_rows", ptr(x), ptr(idx), ptr(out), ll(idx.numel()), c_int(x.shape[1]), stream_ptr())
+    return out
+
+
+def scatter_add_rows_(x, idx, g):
+    require_cuda(x, idx, g)
+    if idx.numel() > 0:
+        call("mm_scatter_add_rows", ptr(x), ptr(idx), ptr(g), ll(idx.numel()), c_int(x.shape[1]), stream_ptr())
+    return x
+
+
+# ------------------------------------------------------------------------------------------------
+# vision feature reduction (K7)
+# ------------------------------------------------------------------------------------------------
+def bilinear_l2norm(x, out_side: int, normalize: bool = True, eps: float = 1e-12):
+    """x [N, S*S, C] bf16 -> [N, out_side^2, C]: bilinear (align_corners=False) + L2 normalise."""
+    require_cuda(x)
+    n, ss, c = x.shape
+    s = int(round(ss ** 0.5))
+    assert s * s == ss and x.is_contiguous()
+    out = torch.empty((n, out_side * out_side, c), dtype=x.dtype, device=x.device)
+    call("mm_bilinear_l2norm", ptr(x), ptr(out), c_int(n), c_int(s), c_int(out_side), c_int(c),
+         c_int(int(normalize)), c_float(eps), stream_ptr())
+    return out
+
+
+def l2norm_rows(x, eps: float = 1e-12, out=None):
+    require_cuda(x)
+    assert x.dim() == 2 and x.is_contiguous()
+    out = torch.empty_like(x) if out is None else out
+    call("mm_l2norm_rows", ptr(x), ptr(out), ll(x.shape[0]), c_int(x.shape[1]), c_float(eps), stream_ptr())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# losses
+# ------------------------------------------------------------------------------------------------
+def ce_fwd_bwd(logits_f32, labels_i32, V, loss_sum, dlogits=None, grad_scale=1.0, lse_out=None,
+               ignore_index=-100):
+    require_cuda(logits_f32, labels_i32, loss_sum)
+    assert logits_f32.dtype == torch.float32 and logits_f32.stride(1) == 1
+    assert labels_i32.dtype == torch.int32
+    R = logits_f32.shape[0]
+    call("mm_ce_fwd_bwd", ptr(logits_f32), ll(logits_f32.stride(0)), ptr(labels_i32), ptr(dlogits),
+         ll(dlogits.stride(0) if dlogits is not None else 0), ptr(loss_sum), ptr(lse_out), ll(R),
+         c_int(V), c_float(grad_scale), c_int(ignore_index), stream_ptr())
+
+
+def cosine_loss(pred, target, loss_sum=None, pred_norm=None, dpred=None, grad_scale=1.0):
+    require_cuda(pred, target)
+    assert pred.is_contiguous() and pred.dim() == 2
+    call("mm_cosine_loss", ptr(pred), ptr(target), ptr(pred_norm), ptr(dpred), ptr(loss_sum),
+         ll(pred.shape[0]), c_int(pred.shape[1]), c_float(grad_scale), stream_ptr())
+
+
+def argmax_rows(logits_f32, V, out=None):
+    require_cuda(logits_f32)
+    R = logits_f32.shape[0]
+    out = torch.empty((R,), dtype=torch.int32, device=logits_f32.device) if out is None else out
+    call("mm_argmax_rows", ptr(logits_f32), ll(logits_f32.stride(0)), ll(R), c_int(V), ptr(out), stream_ptr())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# optimizer
+# ------------------------------------------------------------------------------------------------
+def adamw_step_(p16, p32, m, v, grad, *, lr, beta1, beta2, eps, wd, step, grad_scale=1.0,
+                grad_scale_tensor=None):
+    require_cuda(p16, p32, m, v, grad)
+    n = p32.numel()
+    assert p16.numel() == n and m.numel() == n and v.numel() == n and grad.numel() == n
+    assert p16.is_contiguous() and p32.is_contiguous() and grad.is_contiguous()
+    call("mm_adamw_step", ptr(p16), ptr(p32), ptr(m), ptr(v), ptr(grad),
+         c_int(1 if grad.dtype == torch.float32 else 0), ll(n), c_float(lr), c_float(beta1),
+         c_float(beta2), c_float(eps), c_float(wd), c_int(step), ptr(grad_scale_tensor),
+         c_float(grad_scale), stream_ptr())
+
+
+def clip_coef(sumsq, max_norm):
+    out = torch.empty(2, dtype=torch.float32, device=sumsq.device)
+    call("mm_clip_coef", ptr(sumsq), ptr(out), c_float(max_norm), stream_ptr())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# attention
+# ------------------------------------------------------------------------------------------------
+def attn_fwd(q, k, v, B, T, Hq, Hkv, head_dim, causal, scale, seqlens=None, out=None, need_lse=True):
+    """q/k/v: 2-D row-major views [B*T, *] (may be column slices of one fused QKV buffer)."""
+    require_cuda(q, k, v, seqlens)
+    assert q.stride(1) == 1 and k.stride(1) == 1 and v.stride(1) == 1
+    if out is None:
+        out = torch.empty((B * T, Hq * head_dim), dtype=torch.bfloat16, device=q.device)
+    lse = torch.empty((B, Hq, T), dtype=torch.float32, device=q.device) if need_lse else None
+    call("mm_attn_fwd", ptr(q), ptr(k), ptr(v), ptr(out), ptr(lse), ptr(seqlens), ll(q.stride(0)),
+         ll(k.stride(0)), ll(v.stride(0)), ll(out.stride(0)), c_int(B), c_int(T), c_int(Hq),
+         c_int(Hkv), c_int(head_dim), c_int(int(causal)), c_float(scale), stream_ptr())
+    return out, lse
+
+
+def attn_bwd(q, k, v, o, dout, lse, dq, dk, dv, B, T, Hq, Hkv, head_dim, scale, seqlens=None,
+             workspace=None):
+    require_cuda(q, k, v, o, dout, lse, dq, dk, dv)
+    from ._lib import lib
+    fn = lib().mm_attn_bwd_workspace_bytes
+    fn.restype = ctypes_ll
+    need = fn(c_int(B), c_int(T), c_int(Hq))
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=q.device)
+    call("mm_attn_bwd", ptr(q), ptr(k), ptr(v), ptr(o), ptr(dout), ptr(lse), ptr(dq), ptr(dk), ptr(dv),
+         ptr(seqlens), ll(q.stride(0)), ll(k.stride(0)), ll(v.stride(0)), ll(o.stride(0)),
+         ll(dout.stride(0)), ll(dq.stride(0)), ll(dk.stride(0)), ll(dv.stride(0)), c_int(B), c_int(T),
+         c_int(Hq), c_int(Hkv), c_int(head_dim), c_float(scale), ptr(workspace), ll(workspace.numel()),
+         stream_ptr())
+    return workspace
+
+
+import ctypes as _ctypes  # noqa: E402
+
+ctypes_ll = _ctypes.c_longlong
