@@ -1,0 +1,424 @@
+// metamorph_b200 — KV-cached autoregressive decode step.
+//
+// The reference re-runs the whole prefix every step with no cache (metamorph_llama.py:510,526-535);
+// the mathematically equivalent cached step is HBM-bound: every weight byte is streamed once per
+// step for <= 8 sequences. Kernels:
+//   skinny_gemm   y[m<=8, N] = x[m, K] * W[N, K]^T : weight-streaming with mma.sync m16n8k16 where
+//                 the 16-row operand is a slab of W (rows = output features) and the 8-wide operand
+//                 is the batch. Each lane pulls 2 x 128-bit of W per k32 step straight from HBM in
+//                 fragment order (a k-permutation shared by both operands), 8 warps split K, fp32
+//                 cross-warp reduction in smem, fused bias / residual / GELU / SwiGLU epilogue.
+//   decode_attn   per (sequence, kv head): RoPE on the new q (4 GQA heads) and k, append k/v to the
+//                 cache, single-query attention over the cache, all in one launch.
+//   decode_state  the per-sequence text/image mode state machine of greedy_decode
+//                 (metamorph_llama.py:547-582) on the device: no .item() host syncs.
+#include "common.cuh"
+
+namespace {
+
+constexpr int SK_THREADS = 256;
+enum SkEpi : int { SK_STORE = 0, SK_BIAS = 1, SK_RESID = 2, SK_BIAS_GELU = 3, SK_SWIGLU = 4 };
+
+// ROWS = 16 or 32 weight rows per CTA. x: [8, K] bf16 (rows >= m are ignored via m mask on store).
+template <int ROWS>
+__global__ void __launch_bounds__(SK_THREADS)
+skinny_gemm_kernel(const bf16* __restrict__ x, long long ldx, const bf16* __restrict__ W,
+                   long long ldw, void* __restrict__ y, long long ldy, const bf16* __restrict__ bias,
+                   const bf16* __restrict__ resid, long long ldr, int m, int N, int K, int epi,
+                   int out_f32) {
+  constexpr int G = ROWS / 16;
+  __shared__ float red[SK_THREADS / 32][ROWS][8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int n0 = blockIdx.x * ROWS;
+  float acc[G][4];
+#pragma unroll
+  for (int i = 0; i < G; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const bf16* xrow = x + (long long)g * ldx;  // batch row g (B operand column)
+  const bool xok = g < m;
+  const int nchunks = K >> 5;
+  // warp w handles k32-chunks w, w+8, ...; unrolled by 2 for memory-level parallelism
+  for (int c = warp; c < nchunks; c += 2 * (SK_THREADS / 32)) {
+    const int c2 = c + SK_THREADS / 32;
+    const bool has2 = c2 < nchunks;
+    int4 wa[2][G][2];
+    int4 xb[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int cc = u == 0 ? c : c2;
+      const bool ok = u == 0 || has2;
+      const int k0 = cc * 32 + t * 8;
+#pragma unroll
+      for (int i = 0; i < G; ++i) {
+        const int r0 = n0 + i * 16 + g, r1 = r0 + 8;
+        wa[u][i][0] = (ok && r0 < N) ? ld_nc_int4(W + (long long)r0 * ldw + k0) : make_int4(0, 0, 0, 0);
+        wa[u][i][1] = (ok && r1 < N) ? ld_nc_int4(W + (long long)r1 * ldw + k0) : make_int4(0, 0, 0, 0);
+      }
+      xb[u] = (ok && xok) ? *reinterpret_cast<const int4*>(xrow + k0) : make_int4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+#pragma unroll
+      for (int i = 0; i < G; ++i) {
+        // k-permutation: lane t owns k = 8t..8t+7 of the chunk; MMA #1 uses elements {0,1 | 2,3},
+        // MMA #2 uses {4,5 | 6,7}; the B fragment uses the same slots, so the sum is unchanged.
+        const uint32_t a1[4] = {(uint32_t)wa[u][i][0].x, (uint32_t)wa[u][i][1].x,
+                                (uint32_t)wa[u][i][0].y, (uint32_t)wa[u][i][1].y};
+        const uint32_t a2[4] = {(uint32_t)wa[u][i][0].z, (uint32_t)wa[u][i][1].z,
+                                (uint32_t)wa[u][i][0].w, (uint32_t)wa[u][i][1].w};
+        mma_bf16_16816(acc[i], a1, (uint32_t)xb[u].x, (uint32_t)xb[u].y);
+        mma_bf16_16816(acc[i], a2, (uint32_t)xb[u].z, (uint32_t)xb[u].w);
+      }
+    }
+  }
+  // acc[i]: c0,c1 = (row n = i*16+g, batch 2t,2t+1); c2,c3 = (row n+8, batch 2t,2t+1)
+#pragma unroll
+  for (int i = 0; i < G; ++i) {
+    red[warp][i * 16 + g][2 * t] = acc[i][0];
+    red[warp][i * 16 + g][2 * t + 1] = acc[i][1];
+    red[warp][i * 16 + g + 8][2 * t] = acc[i][2];
+    red[warp][i * 16 + g + 8][2 * t + 1] = acc[i][3];
+  }
+  __syncthreads();
+  if (epi == SK_SWIGLU) {
+    // ROWS == 32: rows [0,16) gate, [16,32) up of the same 16 intermediate channels
+    if (ROWS == 32 && threadIdx.x < 128) {
+      const int r = threadIdx.x >> 3, b = threadIdx.x & 7;
+      float gsum = 0.f, usum = 0.f;
+#pragma unroll
+      for (int w = 0; w < SK_THREADS / 32; ++w) {
+        gsum += red[w][r][b];
+        usum += red[w][r + 16][b];
+      }
+      const int col = (n0 >> 1) + r;
+      if (b < m && n0 + r < N)
+        reinterpret_cast<bf16*>(y)[(long long)b * ldy + col] = __float2bfloat16(silu(gsum) * usum);
+    }
+    return;
+  }
+  for (int idx = threadIdx.x; idx < ROWS * 8; idx += SK_THREADS) {
+    const int r = idx >> 3, b = idx & 7;
+    const int n = n0 + r;
+    if (b >= m || n >= N) continue;
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < SK_THREADS / 32; ++w) s += red[w][r][b];
+    if (epi == SK_BIAS || epi == SK_BIAS_GELU) s += __bfloat162float(bias[n]);
+    if (epi == SK_BIAS_GELU) s = gelu_erf(s);
+    if (epi == SK_RESID) s += __bfloat162float(resid[(long long)b * ldr + n]);
+    if (out_f32) reinterpret_cast<float*>(y)[(long long)b * ldy + n] = s;
+    else reinterpret_cast<bf16*>(y)[(long long)b * ldy + n] = __float2bfloat16(s);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// decode attention. qkv: [B, (Hq+2Hkv)*128] (pre-RoPE) ; cache K/V: [B, Hkv, Tmax, 128]
+// grid (Hkv, B), 128 threads. pos[b] = index of the new token (= number of cached tokens).
+constexpr int DA_THREADS = 128;
+constexpr int DA_D = 128;
+
+__global__ void __launch_bounds__(DA_THREADS)
+decode_attn_kernel(const bf16* __restrict__ qkv, long long ldqkv, bf16* __restrict__ kc,
+                   bf16* __restrict__ vc, const int* __restrict__ pos_arr,
+                   const float* __restrict__ cos_t, const float* __restrict__ sin_t,
+                   bf16* __restrict__ out, long long ldo, int Hq, int Hkv, int Tmax, float scale) {
+  extern __shared__ float sm[];
+  const int G = Hq / Hkv;               // q heads per kv head (<= 8)
+  float* sq = sm;                        // [G][128]
+  float* sscore = sq + G * DA_D;         // [G][Tpad]
+  const int hk = blockIdx.x, b = blockIdx.y;
+  const int pos = pos_arr[b];
+  const int n_ctx = pos + 1;
+  const int Tpad = (Tmax + 3) & ~3;
+  float* sred = sscore + G * Tpad;       // [G][4 warps][128] partial outputs
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bf16* row = qkv + (long long)b * ldqkv;
+  bf16* kcb = kc + ((long long)b * Hkv + hk) * Tmax * DA_D;
+  bf16* vcb = vc + ((long long)b * Hkv + hk) * Tmax * DA_D;
+  const float* cp = cos_t + (long long)pos * (DA_D / 2);
+  const float* sp = sin_t + (long long)pos * (DA_D / 2);
+  // RoPE on q heads -> smem (fp32, pre-scaled), on k -> cache; v -> cache
+  for (int i = tid; i < G * (DA_D / 2); i += DA_THREADS) {
+    const int h = i / (DA_D / 2), j = i % (DA_D / 2);
+    const bf16* qh = row + (long long)(hk * G + h) * DA_D;
+    const float a = __bfloat162float(qh[j]), c = __bfloat162float(qh[j + DA_D / 2]);
+    // bf16 rounding of the rotated q mirrors the training kernel (rope_ writes bf16)
+    sq[h * DA_D + j] = __bfloat162float(__float2bfloat16(a * cp[j] - c * sp[j])) * scale;
+    sq[h * DA_D + j + DA_D / 2] = __bfloat162float(__float2bfloat16(c * cp[j] + a * sp[j])) * scale;
+  }
+  if (tid < DA_D / 2) {
+    const bf16* kh = row + (long long)(Hq + hk) * DA_D;
+    const float a = __bfloat162float(kh[tid]), c = __bfloat162float(kh[tid + DA_D / 2]);
+    kcb[(long long)pos * DA_D + tid] = __float2bfloat16(a * cp[tid] - c * sp[tid]);
+    kcb[(long long)pos * DA_D + tid + DA_D / 2] = __float2bfloat16(c * cp[tid] + a * sp[tid]);
+  } else {
+    const int j = (tid - DA_D / 2) * 2;
+    const bf16* vh = row + (long long)(Hq + Hkv + hk) * DA_D;
+    vcb[(long long)pos * DA_D + j] = vh[j];
+    vcb[(long long)pos * DA_D + j + 1] = vh[j + 1];
+  }
+  __syncthreads();
+  // scores: one thread per cached position
+  for (int p = tid; p < n_ctx; p += DA_THREADS) {
+    const int4* kp = reinterpret_cast<const int4*>(kcb + (long long)p * DA_D);
+    float s[8];
+#pragma unroll
+    for (int h = 0; h < 8; ++h) s[h] = 0.f;
+#pragma unroll 4
+    for (int v = 0; v < DA_D / 8; ++v) {
+      const int4 raw = kp[v];
+      const uint32_t u[4] = {(uint32_t)raw.x, (uint32_t)raw.y, (uint32_t)raw.z, (uint32_t)raw.w};
+      float kf[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2(u[j]);
+        kf[2 * j] = f.x;
+        kf[2 * j + 1] = f.y;
+      }
+      for (int h = 0; h < G; ++h) {
+        const float* qh = sq + h * DA_D + v * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[h] += qh[j] * kf[j];
+      }
+    }
+    for (int h = 0; h < G; ++h) sscore[h * Tpad + p] = s[h];
+  }
+  __syncthreads();
+  // softmax per head (warp h handles head h, h+4, ...)
+  for (int h = warp; h < G; h += DA_THREADS / 32) {
+    float mx = -INFINITY;
+    for (int p = lane; p < n_ctx; p += 32) mx = fmaxf(mx, sscore[h * Tpad + p]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int p = lane; p < n_ctx; p += 32) {
+      const float e = __expf(sscore[h * Tpad + p] - mx);
+      sscore[h * Tpad + p] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    for (int p = lane; p < n_ctx; p += 32) sscore[h * Tpad + p] *= inv;
+  }
+  __syncthreads();
+  // O = P V: lane owns 4 dims, warp w takes positions w, w+4, ...
+  float o[8][4];
+#pragma unroll
+  for (int h = 0; h < 8; ++h)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[h][j] = 0.f;
+  for (int p = warp; p < n_ctx; p += DA_THREADS / 32) {
+    const uint2 raw = *reinterpret_cast<const uint2*>(vcb + (long long)p * DA_D + lane * 4);
+    const float2 f0 = unpack_bf16x2(raw.x), f1 = unpack_bf16x2(raw.y);
+    for (int h = 0; h < G; ++h) {
+      const float pr = sscore[h * Tpad + p];
+      o[h][0] += pr * f0.x; o[h][1] += pr * f0.y; o[h][2] += pr * f1.x; o[h][3] += pr * f1.y;
+    }
+  }
+  for (int h = 0; h < G; ++h)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sred[(h * 4 + warp) * DA_D + lane * 4 + j] = o[h][j];
+  __syncthreads();
+  for (int i = tid; i < G * DA_D; i += DA_THREADS) {
+    const int h = i / DA_D, dcol = i % DA_D;
+    const float s = sred[(h * 4 + 0) * DA_D + dcol] + sred[(h * 4 + 1) * DA_D + dcol] +
+                    sred[(h * 4 + 2) * DA_D + dcol] + sred[(h * 4 + 3) * DA_D + dcol];
+    out[(long long)b * ldo + (long long)(hk * G + h) * DA_D + dcol] = __float2bfloat16(s);
+  }
+}
+
+// copy post-RoPE K/V of a prefill pass (qkv rows [B*T, ld]) into the cache
+__global__ void kv_prefill_kernel(const bf16* __restrict__ qkv, long long ld, bf16* __restrict__ kc,
+                                  bf16* __restrict__ vc, int B, int T, int Hq, int Hkv, int Tmax) {
+  const long long total = (long long)B * T * Hkv * (DA_D / 8);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % (DA_D / 8));
+    long long r = i / (DA_D / 8);
+    const int hk = (int)(r % Hkv);
+    r /= Hkv;
+    const int t = (int)(r % T), b = (int)(r / T);
+    const bf16* src = qkv + ((long long)b * T + t) * ld;
+    const long long dst = (((long long)b * Hkv + hk) * Tmax + t) * DA_D + v * 8;
+    *reinterpret_cast<int4*>(kc + dst) = *reinterpret_cast<const int4*>(src + (long long)(Hq + hk) * DA_D + v * 8);
+    *reinterpret_cast<int4*>(vc + dst) = *reinterpret_cast<const int4*>(src + (long long)(Hq + Hkv + hk) * DA_D + v * 8);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// greedy_decode state machine (metamorph_llama.py:547-582), one thread per sequence.
+struct DecodeState {
+  int* in_image_mode;      // [B]
+  int* total_image_tokens; // [B]
+  int* total_output;       // [B]
+  int* finished;           // [B]
+  int* pos;                // [B] next cache position
+  int* n_ids;              // [B]
+  int* n_img;              // [B]
+  int* ids_out;            // [B, max_ids]
+  int* append_kind;        // [B] out: 0 = token embedding, 1 = predicted visual embedding, -1 = none
+  int* next_token;         // [B] out: token whose embedding is appended (when kind 0)
+};
+
+__global__ void decode_state_kernel(DecodeState st, const int* __restrict__ argmax_tok,
+                                    const int* __restrict__ forced, int forced_ld, int step, int B,
+                                    int num_image_tokens, int max_new_tokens, int max_ids,
+                                    int start_id, int end_id, int eos0, int eos1,
+                                    const bf16* __restrict__ pred_z, bf16* __restrict__ img_out,
+                                    int max_img, int C) {
+  const int b = blockIdx.x;
+  __shared__ int s_store_img;
+  __shared__ int s_slot;
+  if (threadIdx.x == 0) {
+    s_store_img = 0;
+    int kind = -1;
+    if (!st.finished[b]) {
+      const int tok = forced ? forced[(long long)b * forced_ld + step] : argmax_tok[b];
+      const int mode = st.in_image_mode[b];
+      if (!mode && tok == start_id) {
+        st.in_image_mode[b] = 1;
+        if (st.n_ids[b] < max_ids) st.ids_out[(long long)b * max_ids + st.n_ids[b]] = tok;
+        st.n_ids[b]++;
+        kind = 0;
+      } else if (mode && st.total_image_tokens[b] < num_image_tokens) {
+        st.total_image_tokens[b]++;
+        s_store_img = 1;
+        s_slot = st.n_img[b];
+        st.n_img[b]++;
+        kind = 1;
+        if (st.total_image_tokens[b] == num_image_tokens) st.in_image_mode[b] = 0;
+      } else if (tok == end_id) {
+        st.in_image_mode[b] = 0;
+        st.total_image_tokens[b] = 0;
+        if (st.n_ids[b] < max_ids) st.ids_out[(long long)b * max_ids + st.n_ids[b]] = tok;
+        st.n_ids[b]++;
+        kind = 0;
+      } else {
+        if (st.n_ids[b] < max_ids) st.ids_out[(long long)b * max_ids + st.n_ids[b]] = tok;
+        st.n_ids[b]++;
+        kind = 0;
+      }
+      st.total_output[b]++;
+      st.next_token[b] = tok;
+      if (tok == eos0 || tok == eos1) st.finished[b] = 1;
+      else if (st.total_output[b] > max_new_tokens) st.finished[b] = 1;
+      st.pos[b]++;
+    }
+    st.append_kind[b] = kind;
+  }
+  __syncthreads();
+  if (s_store_img && s_slot < max_img) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x)
+      img_out[((long long)b * max_img + s_slot) * C + c] = pred_z[(long long)b * C + c];
+  }
+}
+
+// next input embedding: kind 0 -> embed_tokens[next_token], kind 1 -> prediction row, else keep
+__global__ void decode_next_input_kernel(const int* __restrict__ kind, const int* __restrict__ tok,
+                                         const bf16* __restrict__ embed, const bf16* __restrict__ pred,
+                                         bf16* __restrict__ x, int H) {
+  const int b = blockIdx.x;
+  const int k = kind[b];
+  if (k < 0) return;
+  const bf16* src = k == 0 ? embed + (long long)tok[b] * H : pred + (long long)b * H;
+  for (int v = threadIdx.x; v < H / 8; v += blockDim.x)
+    reinterpret_cast<int4*>(x + (long long)b * H)[v] = reinterpret_cast<const int4*>(src)[v];
+}
+
+// hidden_eff[b] = in_image_mode[b] ? prediction[b] : hidden[b]   (metamorph_llama.py:377)
+__global__ void decode_select_hidden_kernel(const int* __restrict__ mode, const bf16* __restrict__ hidden,
+                                            const bf16* __restrict__ pred, bf16* __restrict__ out, int H) {
+  const int b = blockIdx.x;
+  const bf16* src = mode[b] ? pred + (long long)b * H : hidden + (long long)b * H;
+  for (int v = threadIdx.x; v < H / 8; v += blockDim.x)
+    reinterpret_cast<int4*>(out + (long long)b * H)[v] = reinterpret_cast<const int4*>(src)[v];
+}
+
+}  // namespace
+
+MM_API int mm_skinny_gemm(const void* x, const void* W, void* y, const void* bias, const void* resid,
+                          long long ldx, long long ldw, long long ldy, long long ldr, int m, int N,
+                          int K, int epilogue, int out_f32, cudaStream_t stream) {
+  MM_CHECK_ARG(m >= 1 && m <= 8, "mm_skinny_gemm: batch must be in [1,8] (m=%d)", m);
+  MM_CHECK_ARG(K % 32 == 0 && ldx % 8 == 0 && ldw % 8 == 0, "mm_skinny_gemm: need K%%32==0, ldx/ldw%%8==0");
+  MM_CHECK_ARG(epilogue >= SK_STORE && epilogue <= SK_SWIGLU, "mm_skinny_gemm: bad epilogue");
+  MM_CHECK_ARG((epilogue != SK_BIAS && epilogue != SK_BIAS_GELU) || bias, "mm_skinny_gemm: bias missing");
+  MM_CHECK_ARG(epilogue != SK_RESID || resid, "mm_skinny_gemm: residual missing");
+  const bool rows32 = (epilogue == SK_SWIGLU) || (N >= 32 * 2 * mm_num_sms());
+  if (epilogue == SK_SWIGLU) MM_CHECK_ARG(N % 32 == 0 && !out_f32, "mm_skinny_gemm: SWIGLU needs N%%32==0");
+  if (rows32)
+    skinny_gemm_kernel<32><<<(N + 31) / 32, SK_THREADS, 0, stream>>>(
+        (const bf16*)x, ldx, (const bf16*)W, ldw, y, ldy, (const bf16*)bias, (const bf16*)resid, ldr, m,
+        N, K, epilogue, out_f32);
+  else
+    skinny_gemm_kernel<16><<<(N + 15) / 16, SK_THREADS, 0, stream>>>(
+        (const bf16*)x, ldx, (const bf16*)W, ldw, y, ldy, (const bf16*)bias, (const bf16*)resid, ldr, m,
+        N, K, epilogue, out_f32);
+  MM_CHECK_LAUNCH();
+  return MM_OK;
+}
+
+MM_API int mm_decode_attn(const void* qkv, long long ldqkv, void* kcache, void* vcache, const int* pos,
+                          const float* cos_t, const float* sin_t, void* out, long long ldo, int B,
+                          int Hq, int Hkv, int head_dim, int Tmax, float scale, cudaStream_t stream) {
+  MM_CHECK_ARG(head_dim == DA_D && Hq % Hkv == 0 && Hq / Hkv <= 8, "mm_decode_attn: need head_dim 128, group<=8");
+  const int G = Hq / Hkv;
+  const int Tpad = (Tmax + 3) & ~3;
+  const size_t smem = (size_t)(G * DA_D + G * Tpad + G * 4 * DA_D) * sizeof(float);
+  MM_CHECK_ARG(smem <= 200 * 1024, "mm_decode_attn: Tmax %d too large for the single-pass kernel", Tmax);
+  if (smem > 48 * 1024)
+    MM_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  decode_attn_kernel<<<dim3(Hkv, B), DA_THREADS, smem, stream>>>(
+      (const bf16*)qkv, ldqkv, (bf16*)kcache, (bf16*)vcache, pos, cos_t, sin_t, (bf16*)out, ldo, Hq, Hkv,
+      Tmax, scale);
+  MM_CHECK_LAUNCH();
+  return MM_OK;
+}
+
+MM_API int mm_kv_prefill(const void* qkv, long long ld, void* kcache, void* vcache, int B, int T, int Hq,
+                         int Hkv, int head_dim, int Tmax, cudaStream_t stream) {
+  MM_CHECK_ARG(head_dim == DA_D && T <= Tmax, "mm_kv_prefill: need head_dim 128 and T<=Tmax");
+  const long long total = (long long)B * T * Hkv * (DA_D / 8);
+  long long blocks = ceil_div64(total, 256);
+  if (blocks > (long long)mm_num_sms() * 16) blocks = (long long)mm_num_sms() * 16;
+  kv_prefill_kernel<<<(int)blocks, 256, 0, stream>>>((const bf16*)qkv, ld, (bf16*)kcache, (bf16*)vcache, B,
+                                                     T, Hq, Hkv, Tmax);
+  MM_CHECK_LAUNCH();
+  return MM_OK;
+}
+
+MM_API int mm_decode_state_step(int* in_image_mode, int* total_image_tokens, int* total_output,
+                                int* finished, int* pos, int* n_ids, int* n_img, int* ids_out,
+                                int* append_kind, int* next_token, const int* argmax_tok,
+                                const int* forced, int forced_ld, int step, int B, int num_image_tokens,
+                                int max_new_tokens, int max_ids, int start_id, int end_id, int eos0,
+                                int eos1, const void* pred_z, void* img_out, int max_img, int C,
+                                cudaStream_t stream) {
+  DecodeState st{in_image_mode, total_image_tokens, total_output, finished, pos,
+                 n_ids, n_img, ids_out, append_kind, next_token};
+  decode_state_kernel<<<B, 128, 0, stream>>>(st, argmax_tok, forced, forced_ld, step, B, num_image_tokens,
+                                             max_new_tokens, max_ids, start_id, end_id, eos0, eos1,
+                                             (const bf16*)pred_z, (bf16*)img_out, max_img, C);
+  MM_CHECK_LAUNCH();
+  return MM_OK;
+}
+
+MM_API int mm_decode_next_input(const int* kind, const int* tok, const void* embed, const void* pred,
+                                void* x, int B, int H, cudaStream_t stream) {
+  MM_CHECK_ARG(H % 8 == 0, "mm_decode_next_input: H%%8");
+  decode_next_input_kernel<<<B, 128, 0, stream>>>(kind, tok, (const bf16*)embed, (const bf16*)pred,
+                                                  (bf16*)x, H);
+  MM_CHECK_LAUNCH();
+  return MM_OK;
+}
+
+MM_API int mm_decode_select_hidden(const int* mode, const void* hidden, const void* pred, void* out,
+                                   int B, int H, cudaStream_t stream) {
+  MM_CHECK_ARG(H % 8 == 0, "mm_decode_select_hidden: H%%8");
+  decode_select_hidden_kernel<<<B, 128, 0, stream>>>(mode, (const bf16*)hidden, (const bf16*)pred,
+                                                     (bf16*)out, H);
+  MM_CHECK_LAUNCH();
+  return MM_OK;
+}

@@ -1,0 +1,124 @@
+"""KV-cached greedy decode emitting text tokens and continuous visual-token embeddings.
+
+Semantics = the reference's `greedy_decode` (metamorph_llama.py:502-597) including its quirks (EOS
+test on the logits of the overwritten hidden state while in image mode; the image-token counter is
+only reset by <image_end>), but (a) with a KV cache instead of re-running the growing prefix
+(F6 in SURVEY.md), (b) batched: every sequence carries its own mode state machine on the device,
+(c) without per-step host syncs: the loop polls `finished` once every `poll_every` steps.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from .. import ops
+from ..constants import EOS_TOKEN_IDS, IMAGE_END_TOKEN_ID, IMAGE_START_TOKEN_ID
+from .llama import StackContext
+
+
+class DecodeEngine:
+    def __init__(self, model):
+        self.m = model
+
+    @torch.no_grad()
+    def generate(self, inputs_embeds: torch.Tensor, prompt_lens: Optional[torch.Tensor] = None,
+                 max_new_tokens: int = 1024, start_image_token_id: int = IMAGE_START_TOKEN_ID,
+                 end_image_token_id: int = IMAGE_END_TOKEN_ID, eos_token_id=EOS_TOKEN_IDS,
+                 forced_tokens: Optional[torch.Tensor] = None, poll_every: int = 16,
+                 max_steps: Optional[int] = None):
+        """inputs_embeds [B, P, H] (right-padded to P; prompt_lens[b] valid rows). B <= 8.
+        Returns (ids list per sequence (int32 tensors), image_embeds list per sequence [n, C])."""
+        m = self.m
+        model = m.get_model()
+        stack = m.stack
+        d = stack.dims
+        dev = inputs_embeds.device
+        B, P, H = inputs_embeds.shape
+        assert B <= 8, "decode batch is limited to 8 sequences per step (skinny GEMM tile)"
+        Hq, Hkv, dh = d.n_heads, d.n_kv_heads, d.head_dim
+        L = len(model.layers)
+        ntok = m.get_vision_tower().image_token_len if m.get_vision_tower() is not None else 0
+        C = m.vision_head.fc2.out_features
+        steps_cap = max_new_tokens + 1 if max_steps is None else max_steps
+        Tmax = P + steps_cap + 1
+        stack.ensure_positions(Tmax + 1)
+        if prompt_lens is None:
+            prompt_lens = torch.full((B,), P, dtype=torch.int32)
+        prompt_lens_dev = prompt_lens.to(dev, dtype=torch.int32)
+        eos = list(eos_token_id) if isinstance(eos_token_id, (list, tuple)) else [eos_token_id]
+        eos0, eos1 = eos[0], (eos[1] if len(eos) > 1 else eos[0])
+
+        kc = torch.zeros((L, B, Hkv, Tmax, dh), dtype=torch.bfloat16, device=dev)
+        vc = torch.zeros_like(kc)
+
+        # ---- prefill: full-sequence kernels, K/V captured into the cache
+        pos = torch.arange(P, dtype=torch.int32).repeat(B).to(dev)
+        ctx = StackContext(B=B, T=P, pos=pos, seqlens=prompt_lens_dev)
+        layers = [l.weights() for l in model.layers]
+        x = inputs_embeds.reshape(B * P, H).contiguous()
+        for i, w in enumerate(layers):
+            x = stack.layer_forward(w, x, ctx, save=True, save_gu=False)
+            s = ctx.saved.pop()
+            ops.kv_prefill(s.qkv, kc[i], vc[i], B, P, Hq, Hkv, dh)
+            del s
+        last_rows = (torch.arange(B, dtype=torch.int32) * P + (prompt_lens.to(torch.int32) - 1)).to(dev)
+        h_last = ops.gather_rows(x, last_rows)                      # [B, H] pre-final-norm
+        del x
+
+        st = {k: torch.zeros(B, dtype=torch.int32, device=dev) for k in
+              ("in_image_mode", "total_image_tokens", "total_output", "finished", "n_ids", "n_img",
+               "append_kind", "next_token")}
+        st["pos"] = prompt_lens_dev.clone()
+        max_img = max(1, (steps_cap // max(ntok, 1) + 1) * max(ntok, 1))
+        st["ids_out"] = torch.full((B, steps_cap + 1), -1, dtype=torch.int32, device=dev)
+        img_out = torch.zeros((B, max_img, C), dtype=torch.bfloat16, device=dev)
+        forced = forced_tokens.to(dev, dtype=torch.int32).contiguous() if forced_tokens is not None else None
+        xin = torch.empty((B, H), dtype=torch.bfloat16, device=dev)
+        V = m.lm_head.weight.shape[0]
+        logits = torch.empty((B, (V + 7) // 8 * 8), dtype=torch.float32, device=dev)
+
+        def heads_and_state(h_pre_norm, step):
+            hidden = ops.rmsnorm(h_pre_norm, model.norm.weight.data, d.rms_eps)
+            # image-mode branch computed for every sequence, selected per sequence (graph friendly)
+            vh, pj = m.vision_head, model.mm_projector
+            z = ops.skinny_gemm(hidden, vh.fc1.weight.data, bias=vh.fc1.bias.data, epilogue=ops.SK_BIAS_GELU)
+            z = ops.skinny_gemm(z, vh.fc2.weight.data, bias=vh.fc2.bias.data, epilogue=ops.SK_BIAS)
+            pred_z = ops.l2norm_rows(z) if m.normalize_vision else z
+            p1 = ops.skinny_gemm(pred_z, pj.fc1.weight.data, bias=pj.fc1.bias.data, epilogue=ops.SK_BIAS_GELU)
+            prediction = ops.skinny_gemm(p1, pj.fc2.weight.data, bias=pj.fc2.bias.data, epilogue=ops.SK_BIAS)
+            h_eff = torch.empty_like(hidden)
+            ops.decode_select_hidden(st["in_image_mode"], hidden, prediction, h_eff)
+            ops.skinny_gemm(h_eff, m.lm_head.weight.data, out=logits[:, :V])
+            tok = ops.argmax_rows(logits, V)
+            ops.decode_state_step(st, tok, forced, step, B, ntok, max_new_tokens, start_image_token_id,
+                                  end_image_token_id, eos0, eos1, pred_z, img_out)
+            ops.decode_next_input(st["append_kind"], st["next_token"], model.embed_tokens.weight.data,
+                                  prediction, xin)
+
+        heads_and_state(h_last, 0)
+        step = 1
+        while step < steps_cap:
+            if step % poll_every == 0 and bool(st["finished"].all()):
+                break
+            # position of the token being fed = pos - 1 (state step already advanced pos)
+            cur_pos = st["pos"] - 1
+            x = xin
+            for i, w in enumerate(layers):
+                n1 = ops.rmsnorm(x, w.ln1, d.rms_eps)
+                qkv = ops.skinny_gemm(n1, w.wqkv)
+                attn = ops.decode_attn(qkv, kc[i], vc[i], cur_pos, stack.cos, stack.sin, Hq, Hkv, dh, stack.scale)
+                hmid = ops.skinny_gemm(attn, w.wo, resid=x, epilogue=ops.SK_RESID)
+                n2 = ops.rmsnorm(hmid, w.ln2, d.rms_eps)
+                act = ops.skinny_gemm(n2, w.wgu, epilogue=ops.SK_SWIGLU)
+                x = ops.skinny_gemm(act, w.wd, resid=hmid, epilogue=ops.SK_RESID)
+            heads_and_state(x, step)
+            step += 1
+
+        n_ids = st["n_ids"].cpu().tolist()
+        n_img = st["n_img"].cpu().tolist()
+        ids_cpu = st["ids_out"]
+        out_ids = [ids_cpu[b, :n_ids[b]].clone() for b in range(B)]
+        out_img = [img_out[b, :n_img[b]].clone() for b in range(B)]
+        self.last_steps = step
+        return out_ids, out_img

@@ -299,3 +299,62 @@ def attn_bwd(q, k, v, o, dout, lse, dq, dk, dv, B, T, Hq, Hkv, head_dim, scale, 
 import ctypes as _ctypes  # noqa: E402
 
 ctypes_ll = _ctypes.c_longlong
+
+
+# ------------------------------------------------------------------------------------------------
+# decode (KV-cached step)
+# ------------------------------------------------------------------------------------------------
+SK_STORE, SK_BIAS, SK_RESID, SK_BIAS_GELU, SK_SWIGLU = range(5)
+
+
+def skinny_gemm(x, w, *, bias=None, resid=None, epilogue=SK_STORE, out=None, out_dtype=torch.bfloat16):
+    """y[m<=8, N] = x[m, K] w[N, K]^T — HBM-bound weight streaming for the decode step."""
+    require_cuda(x, w, bias, resid, out)
+    m, K = x.shape
+    N = w.shape[0]
+    n_out = N // 2 if epilogue == SK_SWIGLU else N
+    if out is None:
+        out = torch.empty((m, n_out), dtype=out_dtype, device=x.device)
+    call("mm_skinny_gemm", ptr(x), ptr(w), ptr(out), ptr(bias), ptr(resid), ll(x.stride(0)),
+         ll(w.stride(0)), ll(out.stride(0)), ll(resid.stride(0) if resid is not None else 0), c_int(m),
+         c_int(N), c_int(K), c_int(epilogue), c_int(1 if out.dtype == torch.float32 else 0), stream_ptr())
+    return out
+
+
+def decode_attn(qkv, kcache, vcache, pos, cos, sin, Hq, Hkv, head_dim, scale, out=None):
+    require_cuda(qkv, kcache, vcache, pos, cos, sin)
+    B = qkv.shape[0]
+    Tmax = kcache.shape[2]
+    if out is None:
+        out = torch.empty((B, Hq * head_dim), dtype=torch.bfloat16, device=qkv.device)
+    call("mm_decode_attn", ptr(qkv), ll(qkv.stride(0)), ptr(kcache), ptr(vcache), ptr(pos), ptr(cos),
+         ptr(sin), ptr(out), ll(out.stride(0)), c_int(B), c_int(Hq), c_int(Hkv), c_int(head_dim),
+         c_int(Tmax), c_float(scale), stream_ptr())
+    return out
+
+
+def kv_prefill(qkv, kcache, vcache, B, T, Hq, Hkv, head_dim):
+    require_cuda(qkv, kcache, vcache)
+    call("mm_kv_prefill", ptr(qkv), ll(qkv.stride(0)), ptr(kcache), ptr(vcache), c_int(B), c_int(T),
+         c_int(Hq), c_int(Hkv), c_int(head_dim), c_int(kcache.shape[2]), stream_ptr())
+
+
+def decode_state_step(st: dict, argmax_tok, forced, step, B, num_image_tokens, max_new_tokens,
+                      start_id, end_id, eos0, eos1, pred_z, img_out):
+    call("mm_decode_state_step", ptr(st["in_image_mode"]), ptr(st["total_image_tokens"]),
+         ptr(st["total_output"]), ptr(st["finished"]), ptr(st["pos"]), ptr(st["n_ids"]), ptr(st["n_img"]),
+         ptr(st["ids_out"]), ptr(st["append_kind"]), ptr(st["next_token"]), ptr(argmax_tok), ptr(forced),
+         c_int(forced.stride(0) if forced is not None else 0), c_int(step), c_int(B),
+         c_int(num_image_tokens), c_int(max_new_tokens), c_int(st["ids_out"].shape[1]), c_int(start_id),
+         c_int(end_id), c_int(eos0), c_int(eos1), ptr(pred_z), ptr(img_out), c_int(img_out.shape[1]),
+         c_int(img_out.shape[2]), stream_ptr())
+
+
+def decode_next_input(kind, tok, embed_w, pred, x):
+    call("mm_decode_next_input", ptr(kind), ptr(tok), ptr(embed_w), ptr(pred), ptr(x), c_int(x.shape[0]),
+         c_int(x.shape[1]), stream_ptr())
+
+
+def decode_select_hidden(mode, hidden, pred, out):
+    call("mm_decode_select_hidden", ptr(mode), ptr(hidden), ptr(pred), ptr(out), c_int(out.shape[0]),
+         c_int(out.shape[1]), stream_ptr())
