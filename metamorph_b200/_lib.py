@@ -53,10 +53,23 @@ def ll(x) -> c_longlong:
     return c_longlong(int(x))
 
 
+# kernels launched per C-ABI call (for bench.py's `gpu_launches` claim); default 1
+_LAUNCHES = {"mm_attn_bwd": 3, "mm_clip_coef": 1}
+launch_count = 0
+
+
 def call(name: str, *args) -> None:
+    global launch_count
     fn = getattr(lib(), name)
     fn.restype = c_int
     check(fn(*args), name)
+    launch_count += _LAUNCHES.get(name, 1)
+
+
+def reset_launch_count() -> int:
+    global launch_count
+    n, launch_count = launch_count, 0
+    return n
 
 
 def require_cuda(*tensors) -> None:
@@ -67,5 +80,5 @@ def require_cuda(*tensors) -> None:
                 "There is no CPU fallback on the product path.")
 
 
-__all__ = ["lib", "call", "check", "ptr", "ll", "stream_ptr", "require_cuda", "MetaMorphB200Error",
+__all__ = ["lib", "call", "reset_launch_count", "check", "ptr", "ll", "stream_ptr", "require_cuda", "MetaMorphB200Error",
            "c_int", "c_float", "c_longlong", "c_void_p"]

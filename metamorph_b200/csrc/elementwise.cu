@@ -205,8 +205,9 @@ MM_API int mm_colsum_accum(const void* x, float* out, long long R, long long N, 
 
 MM_API int mm_im2col_patch14(const void* img, void* out, int n_img, int image_size, int ldp,
                              cudaStream_t stream) {
-  MM_CHECK_ARG(n_img > 0 && image_size % 14 == 0 && ldp >= 588 && ldp % 8 == 0,
-               "mm_im2col_patch14: need image_size%%14==0, ldp>=588, ldp%%8==0");
+  // Conv2d(k=14, s=14, padding="valid"): floor(S/14) patches per side (384 -> 27, last 6 px unused)
+  MM_CHECK_ARG(n_img > 0 && image_size >= 14 && ldp >= 588 && ldp % 8 == 0,
+               "mm_im2col_patch14: need image_size>=14, ldp>=588, ldp%%8==0");
   const int G = image_size / 14;
   const long long total = (long long)n_img * G * G * ldp;
   im2col_patch14_kernel<<<ew_grid(total, 256), 256, 0, stream>>>((const bf16*)img, (bf16*)out, n_img,

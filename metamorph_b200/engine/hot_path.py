@@ -10,14 +10,16 @@ autograd graph — so the optimizer can be fused into the backward sweep (engine
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Dict, List, Optional
+from typing import TYPE_CHECKING, Dict, List, Optional
 
 import torch
 
 from .. import ops
 from ..constants import IGNORE_INDEX
-from ..model.interleave_plan import InterleavePlan
 from .llama import LayerGrads, StackContext
+
+if TYPE_CHECKING:  # avoid a model <-> engine import cycle
+    from ..model.interleave_plan import InterleavePlan
 
 
 class GradProvider:

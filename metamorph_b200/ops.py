@@ -11,6 +11,10 @@ from ._lib import call, c_float, c_int, ll, ptr, require_cuda, stream_ptr
 EPI_STORE, EPI_BIAS, EPI_BIAS_GELU_ERF, EPI_BIAS_GELU_TANH, EPI_RESID, EPI_BIAS_RESID, EPI_SWIGLU = range(7)
 
 
+# bench.py instrumentation: when a list, every GEMM launch appends (start_event, end_event, flops)
+GEMM_PROFILE = None
+
+
 def _ld(t: torch.Tensor) -> int:
     assert t.dim() == 2 and t.stride(1) == 1, "expected a row-major 2-D view"
     return t.stride(0)
@@ -40,12 +44,20 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     if out is None:
         out = torch.empty((M, n_out), dtype=out_dtype, device=a.device)
     assert out.shape == (M, n_out) and out.dtype == out_dtype
+    prof = GEMM_PROFILE
+    if prof is not None:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e0.record()
     call("mm_gemm_bf16", ptr(a), ptr(b), ptr(out), ptr(bias), ptr(resid), ptr(aux),
          ll(M), ll(N), ll(K), ll(_ld(a)), ll(_ld(b)), ll(_ld(out)),
          ll(_ld(resid) if resid is not None else 0), ll(_ld(aux) if aux is not None else 0),
          c_int(int(a_mn)), c_int(int(b_mn)), c_int(epilogue),
          c_int(1 if out_dtype == torch.float32 else 0), c_int(int(accumulate)), c_float(alpha),
          c_int(force_bn), stream_ptr())
+    if prof is not None:
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        prof.append((e0, e1, 2.0 * M * N * K))
     return out
 
 
