@@ -275,7 +275,9 @@ __global__ void decode_state_kernel(DecodeState st, const int* __restrict__ argm
     s_store_img = 0;
     int kind = -1;
     if (!st.finished[b]) {
-      const int tok = forced ? forced[(long long)b * forced_ld + step] : argmax_tok[b];
+      // forced schedule is indexed by this sequence's own step count (device-resident -> graph replayable)
+      const int fidx = st.total_output[b] < forced_ld ? st.total_output[b] : forced_ld - 1;
+      const int tok = forced ? forced[(long long)b * forced_ld + fidx] : argmax_tok[b];
       const int mode = st.in_image_mode[b];
       if (!mode && tok == start_id) {
         st.in_image_mode[b] = 1;

@@ -20,6 +20,7 @@ from .llama import StackContext
 class DecodeEngine:
     def __init__(self, model):
         self.m = model
+        self.use_cuda_graph = True
 
     @torch.no_grad()
     def generate(self, inputs_embeds: torch.Tensor, prompt_lens: Optional[torch.Tensor] = None,
@@ -97,11 +98,9 @@ class DecodeEngine:
                                   prediction, xin)
 
         heads_and_state(h_last, 0)
-        step = 1
-        while step < steps_cap:
-            if step % poll_every == 0 and bool(st["finished"].all()):
-                break
-            # position of the token being fed = pos - 1 (state step already advanced pos)
+
+        def one_step_body():
+            # position of the token being fed = pos - 1 (the state step already advanced pos)
             cur_pos = st["pos"] - 1
             x = xin
             for i, w in enumerate(layers):
@@ -112,7 +111,31 @@ class DecodeEngine:
                 n2 = ops.rmsnorm(hmid, w.ln2, d.rms_eps)
                 act = ops.skinny_gemm(n2, w.wgu, epilogue=ops.SK_SWIGLU)
                 x = ops.skinny_gemm(act, w.wd, resid=hmid, epilogue=ops.SK_RESID)
-            heads_and_state(x, step)
+            return x
+
+        # One captured CUDA graph is replayed for every step (launch-bound inner loop): all per-step state,
+        # including the index into the forced-token schedule, lives in device memory.
+        step = 1
+        graph = None
+        if self.use_cuda_graph and steps_cap > 2:
+            heads_and_state(one_step_body(), 1)              # eager warm-up step (sets kernel attributes)
+            step = 2
+            try:
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    heads_and_state(one_step_body(), 0)
+                graph = g
+            except Exception:  # noqa: BLE001 - capture unsupported: stay on stream launches
+                graph = None
+                torch.cuda.synchronize()
+        while step < steps_cap:
+            if step % poll_every == 0 and bool(st["finished"].all()):
+                break
+            if graph is not None:
+                graph.replay()
+            else:
+                heads_and_state(one_step_body(), step)
             step += 1
 
         n_ids = st["n_ids"].cpu().tolist()
