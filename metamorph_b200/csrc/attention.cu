@@ -556,6 +556,27 @@ int launch_fwd(const FwdParams& p, cudaStream_t stream) {
 
 }  // namespace
 
+// Shared by the mma.sync and tcgen05 backward paths (declared in common.cuh).
+int mm_attn_bwd_delta_launch(const void* o, const void* dout, float* delta, long long ldo, long long lddo,
+                             int B, int T, int Hq, int head_dim, cudaStream_t stream) {
+  const long long total = (long long)B * T * Hq;
+  long long blocks = ceil_div64(total, 8);
+  if (blocks > (long long)mm_num_sms() * 16) blocks = (long long)mm_num_sms() * 16;
+  attn_delta_kernel<<<(int)blocks, 256, 0, stream>>>((const bf16*)o, (const bf16*)dout, delta, ldo, lddo, B, T,
+                                                     Hq, head_dim);
+  MM_CHECK_LAUNCH();
+  return MM_OK;
+}
+
+int mm_attn_bwd_convert_launch(const float* dq_accum, void* dq, long long R, int C, long long lddq,
+                               cudaStream_t stream) {
+  long long blocks = ceil_div64(R * (C / 8), 256);
+  if (blocks > (long long)mm_num_sms() * 16) blocks = (long long)mm_num_sms() * 16;
+  f32_to_bf16_rows_kernel<<<(int)blocks, 256, 0, stream>>>(dq_accum, (bf16*)dq, R, C, lddq);
+  MM_CHECK_LAUNCH();
+  return MM_OK;
+}
+
 MM_API int mm_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse,
                        const int* seqlens, long long ldq, long long ldk, long long ldv,
                        long long ldo, int B, int T, int Hq, int Hkv, int head_dim, int causal,

@@ -47,6 +47,10 @@ void mm_set_error(const char* fmt, ...);
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 int mm_num_sms();
+int mm_attn_bwd_delta_launch(const void* o, const void* dout, float* delta, long long ldo, long long lddo,
+                             int B, int T, int Hq, int head_dim, cudaStream_t stream);
+int mm_attn_bwd_convert_launch(const float* dq_accum, void* dq, long long R, int C, long long lddq,
+                               cudaStream_t stream);
 
 // ----------------------------------------------------------------------------------------------
 // Device helpers

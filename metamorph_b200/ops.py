@@ -11,6 +11,8 @@ from ._lib import call, c_float, c_int, ll, ptr, require_cuda, stream_ptr
 EPI_STORE, EPI_BIAS, EPI_BIAS_GELU_ERF, EPI_BIAS_GELU_TANH, EPI_RESID, EPI_BIAS_RESID, EPI_SWIGLU = range(7)
 
 
+ATTN_BWD_TC = True  # tcgen05 backward (csrc/attention_tc.cu); the mma.sync kernel stays selectable with tc=False
+
 # bench.py instrumentation: when a list, every GEMM launch appends (start_event, end_event, flops)
 GEMM_PROFILE = None
 
@@ -278,21 +280,23 @@ def clip_coef(sumsq, max_norm):
 # ------------------------------------------------------------------------------------------------
 # attention
 # ------------------------------------------------------------------------------------------------
-def attn_fwd(q, k, v, B, T, Hq, Hkv, head_dim, causal, scale, seqlens=None, out=None, need_lse=True):
+def attn_fwd(q, k, v, B, T, Hq, Hkv, head_dim, causal, scale, seqlens=None, out=None, need_lse=True,
+             tc=None):
     """q/k/v: 2-D row-major views [B*T, *] (may be column slices of one fused QKV buffer)."""
     require_cuda(q, k, v, seqlens)
     assert q.stride(1) == 1 and k.stride(1) == 1 and v.stride(1) == 1
     if out is None:
         out = torch.empty((B * T, Hq * head_dim), dtype=torch.bfloat16, device=q.device)
     lse = torch.empty((B, Hq, T), dtype=torch.float32, device=q.device) if need_lse else None
-    call("mm_attn_fwd", ptr(q), ptr(k), ptr(v), ptr(out), ptr(lse), ptr(seqlens), ll(q.stride(0)),
+    use_tc = (head_dim == 128) if tc is None else tc
+    call("mm_attn_fwd_tc" if use_tc else "mm_attn_fwd", ptr(q), ptr(k), ptr(v), ptr(out), ptr(lse), ptr(seqlens), ll(q.stride(0)),
          ll(k.stride(0)), ll(v.stride(0)), ll(out.stride(0)), c_int(B), c_int(T), c_int(Hq),
          c_int(Hkv), c_int(head_dim), c_int(int(causal)), c_float(scale), stream_ptr())
     return out, lse
 
 
 def attn_bwd(q, k, v, o, dout, lse, dq, dk, dv, B, T, Hq, Hkv, head_dim, scale, seqlens=None,
-             workspace=None):
+             workspace=None, tc=None):
     require_cuda(q, k, v, o, dout, lse, dq, dk, dv)
     from ._lib import lib
     fn = lib().mm_attn_bwd_workspace_bytes
@@ -300,7 +304,8 @@ def attn_bwd(q, k, v, o, dout, lse, dq, dk, dv, B, T, Hq, Hkv, head_dim, scale, 
     need = fn(c_int(B), c_int(T), c_int(Hq))
     if workspace is None or workspace.numel() < need:
         workspace = torch.empty(need, dtype=torch.uint8, device=q.device)
-    call("mm_attn_bwd", ptr(q), ptr(k), ptr(v), ptr(o), ptr(dout), ptr(lse), ptr(dq), ptr(dk), ptr(dv),
+    use_tc = ATTN_BWD_TC if tc is None else tc
+    call("mm_attn_bwd_tc" if use_tc else "mm_attn_bwd", ptr(q), ptr(k), ptr(v), ptr(o), ptr(dout), ptr(lse), ptr(dq), ptr(dk), ptr(dv),
          ptr(seqlens), ll(q.stride(0)), ll(k.stride(0)), ll(v.stride(0)), ll(o.stride(0)),
          ll(dout.stride(0)), ll(dq.stride(0)), ll(dk.stride(0)), ll(dv.stride(0)), c_int(B), c_int(T),
          c_int(Hq), c_int(Hkv), c_int(head_dim), c_float(scale), ptr(workspace), ll(workspace.numel()),

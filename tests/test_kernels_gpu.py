@@ -266,9 +266,13 @@ def _attn_ref(q, k, v, causal, scale, seqlens=None):
     return torch.einsum("bhqk,bkhd->bqhd", p, v)
 
 
+@pytest.mark.parametrize("tc", [False, True])
 @pytest.mark.parametrize("B,T,Hq,Hkv,d,causal", [(2, 300, 8, 2, 128, True), (1, 1024, 4, 4, 128, True),
-                                                 (2, 729, 4, 4, 72, False), (1, 200, 2, 2, 64, False)])
-def test_attention_fwd(cuda_device, B, T, Hq, Hkv, d, causal):
+                                                 (2, 729, 4, 4, 72, False), (1, 200, 2, 2, 64, False),
+                                                 (2, 640, 4, 2, 128, False)])
+def test_attention_fwd(cuda_device, B, T, Hq, Hkv, d, causal, tc):
+    if tc and d != 128:
+        pytest.skip("tcgen05 attention is specialised for head_dim 128")
     from metamorph_b200 import ops
     torch.manual_seed(10)
     qkv = torch.randn(B * T, (Hq + 2 * Hkv) * d, device=cuda_device).bfloat16()
@@ -277,7 +281,7 @@ def test_attention_fwd(cuda_device, B, T, Hq, Hkv, d, causal):
     seqlens = None
     if causal:
         seqlens = torch.tensor([T, max(1, T - 77)][:B], device=cuda_device, dtype=torch.int32)
-    out, lse = ops.attn_fwd(q, k, v, B, T, Hq, Hkv, d, causal, scale, seqlens=seqlens)
+    out, lse = ops.attn_fwd(q, k, v, B, T, Hq, Hkv, d, causal, scale, seqlens=seqlens, tc=tc)
     ref = _attn_ref(q.float().view(B, T, Hq, d), k.float().view(B, T, Hkv, d), v.float().view(B, T, Hkv, d),
                     causal, scale, seqlens)
     o = out.view(B, T, Hq, d).float()
@@ -289,8 +293,9 @@ def test_attention_fwd(cuda_device, B, T, Hq, Hkv, d, causal):
         _close(o, ref, 2e-2, "attn fwd")
 
 
-@pytest.mark.parametrize("B,T,Hq,Hkv", [(2, 200, 8, 2), (1, 512, 4, 1)])
-def test_attention_bwd(cuda_device, B, T, Hq, Hkv):
+@pytest.mark.parametrize("tc", [False, True])
+@pytest.mark.parametrize("B,T,Hq,Hkv", [(2, 200, 8, 2), (1, 512, 4, 1), (1, 384, 2, 2)])
+def test_attention_bwd(cuda_device, B, T, Hq, Hkv, tc):
     from metamorph_b200 import ops
     torch.manual_seed(11)
     d = 128
@@ -305,7 +310,7 @@ def test_attention_bwd(cuda_device, B, T, Hq, Hkv):
         dout.view(B, T, -1)[b, int(seqlens[b]):] = 0
     dqkv = torch.zeros_like(qkv)
     ops.attn_bwd(q, k, v, out, dout, lse, dqkv[:, :Hq * d], dqkv[:, Hq * d:(Hq + Hkv) * d],
-                 dqkv[:, (Hq + Hkv) * d:], B, T, Hq, Hkv, d, scale, seqlens=seqlens)
+                 dqkv[:, (Hq + Hkv) * d:], B, T, Hq, Hkv, d, scale, seqlens=seqlens, tc=tc)
     qf = q.float().view(B, T, Hq, d).clone().requires_grad_(True)
     kf = k.float().view(B, T, Hkv, d).clone().requires_grad_(True)
     vf = v.float().view(B, T, Hkv, d).clone().requires_grad_(True)
