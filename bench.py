@@ -35,7 +35,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=4, help="samples per GPU")
     ap.add_argument("--seq-len", type=int, default=4096)
     ap.add_argument("--layers", type=int, default=32, help="debug only: fewer layers => invalid as a result")
-    ap.add_argument("--save-gu-layers", type=int, default=int(os.environ.get("MM_SAVE_GU_LAYERS", "16")))
+    ap.add_argument("--save-gu-layers", type=int, default=int(os.environ.get("MM_SAVE_GU_LAYERS", "32")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
@@ -349,7 +349,8 @@ def main():
                            "l2_policy": "inputs+weights (>100 GB/step) far exceed the 126 MB L2; no flush needed",
                            "max_grad_norm": None, "optimizer": "AdamW (fused into backward, fp32 master/m/v)",
                            "recompute": f"gate/up GEMM recomputed in {args.layers - min(args.save_gu_layers, args.layers)} of {args.layers} layers; norms always",
-                           "loss": loss_val},
+                           "loss": loss_val,
+                           "peak_hbm_gb": round(torch.cuda.max_memory_allocated() / 1e9, 1)},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "decode": decode, "gpu_launches": launches, "clocks": clocks}
         print(json.dumps(line), flush=True)
     if world > 1:

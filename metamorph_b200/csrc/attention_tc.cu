@@ -63,6 +63,11 @@ __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_
       "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void tmem_st_wait() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
@@ -294,6 +299,226 @@ flash_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Forward v2: 1 CTA/SM, 16 softmax warps (warp -> TMEM lane quadrant x 32-column chunk), S double-buffered
+// in TMEM so the tensor core computes S_{j+1} while the CUDA cores run softmax_j, K/V double-buffered in
+// smem. One TMEM pass over S per tile (values stay in registers), one named barrier per tile to exchange the
+// row maxima of the four column chunks.
+// ---------------------------------------------------------------------------------------------------
+constexpr int TC2_THREADS = 576;
+constexpr int TC2_SMEM = 5 * TC_TILE_BYTES + 2 * 4 * 128 * 4 + 4 * 128 * 4 + 256 + 1024;
+
+__global__ void __launch_bounds__(TC2_THREADS, 1)
+flash_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                     const __grid_constant__ CUtensorMap tmap_v, TcFwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sQ = base;
+  const uint32_t sK[2] = {base + TC_TILE_BYTES, base + 2 * TC_TILE_BYTES};
+  const uint32_t sV[2] = {base + 3 * TC_TILE_BYTES, base + 4 * TC_TILE_BYTES};
+  float* sMax = reinterpret_cast<float*>(base_ptr + 5 * TC_TILE_BYTES);   // [2][4][128]
+  float* sSum = sMax + 2 * 4 * 128;                                       // [4][128]
+  const uint32_t bar = base + 5 * TC_TILE_BYTES + 2 * 4 * 128 * 4 + 4 * 128 * 4;
+  const uint32_t q_full = bar, k_full0 = bar + 8, k_full1 = bar + 16, k_empty0 = bar + 24, k_empty1 = bar + 32,
+                 v_full0 = bar + 40, v_full1 = bar + 48, v_empty0 = bar + 56, v_empty1 = bar + 64,
+                 s_full0 = bar + 72, s_full1 = bar + 80, p_full0 = bar + 88, p_full1 = bar + 96,
+                 o_done = bar + 104, tmem_slot = bar + 112;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
+      base_ptr + 5 * TC_TILE_BYTES + 2 * 4 * 128 * 4 + 4 * 128 * 4 + 112);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = (int)gridDim.x - 1 - (int)blockIdx.x;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int hk = h / (p.Hq / p.Hkv);
+  const int q0 = qt * TC_BR;
+  const int kv_len = p.seqlens ? p.seqlens[b] : p.T;
+  int kv_end = kv_len;
+  if (p.causal) kv_end = min(kv_end, q0 + TC_BR);
+  const int n_tiles = (kv_end + TC_BC - 1) / TC_BC;
+  const int tok0 = b * p.T;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_q);
+    prefetch_tmap(&tmap_k);
+    prefetch_tmap(&tmap_v);
+    for (int i = 0; i < 9; ++i) mbar_init(bar + 8 * i, 1);   // q_full .. v_empty1
+    mbar_init(s_full0, 1);
+    mbar_init(s_full1, 1);
+    mbar_init(p_full0, 16);
+    mbar_init(p_full1, 16);
+    mbar_init(o_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  const uint32_t tSb[2] = {tmem, tmem + 128};
+  const uint32_t tO = tmem + 256;
+
+  if (warp == 0 && lane == 0) {
+    if (n_tiles > 0) {
+      mbar_arrive_expect_tx(q_full, TC_TILE_BYTES);
+      tma_load_2d(sQ, &tmap_q, q_full, h * TC_D, tok0 + q0);
+      tma_load_2d(sQ + 16384, &tmap_q, q_full, h * TC_D + 64, tok0 + q0);
+    }
+    for (int j = 0; j < n_tiles; ++j) {
+      const int bf = j & 1;
+      const uint32_t ph = (uint32_t)((j >> 1) & 1);
+      mbar_wait(bf ? k_empty1 : k_empty0, ph ^ 1);
+      mbar_arrive_expect_tx(bf ? k_full1 : k_full0, TC_TILE_BYTES);
+      tma_load_2d(sK[bf], &tmap_k, bf ? k_full1 : k_full0, hk * TC_D, tok0 + j * TC_BC);
+      tma_load_2d(sK[bf] + 16384, &tmap_k, bf ? k_full1 : k_full0, hk * TC_D + 64, tok0 + j * TC_BC);
+      mbar_wait(bf ? v_empty1 : v_empty0, ph ^ 1);
+      mbar_arrive_expect_tx(bf ? v_full1 : v_full0, TC_TILE_BYTES);
+      tma_load_2d(sV[bf], &tmap_v, bf ? v_full1 : v_full0, hk * TC_D, tok0 + j * TC_BC);
+      tma_load_2d(sV[bf] + 16384, &tmap_v, bf ? v_full1 : v_full0, hk * TC_D + 64, tok0 + j * TC_BC);
+    }
+  } else if (warp == 1 && lane == 0) {
+    const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(TC_BC >> 3) << 17) |
+                             (uint32_t(TC_BR >> 4) << 24);
+    const uint32_t idesc_o = idesc_s | (1u << 16);
+    auto issue_s = [&](int j) {
+      const int bf = j & 1;
+      mbar_wait(bf ? k_full1 : k_full0, (uint32_t)((j >> 1) & 1));
+      tcgen05_fence_after();
+#pragma unroll
+      for (int k = 0; k < TC_D / 16; ++k)
+        umma_bf16_ss(tSb[bf], desc_kmajor(sQ, k), desc_kmajor(sK[bf], k), idesc_s, k != 0 ? 1u : 0u);
+      umma_commit(bf ? k_empty1 : k_empty0);
+      umma_commit(bf ? s_full1 : s_full0);
+    };
+    if (n_tiles > 0) {
+      mbar_wait(q_full, 0);
+      issue_s(0);
+    }
+    for (int j = 0; j < n_tiles; ++j) {
+      const int bf = j & 1;
+      const uint32_t ph = (uint32_t)((j >> 1) & 1);
+      if (j + 1 < n_tiles) {
+        // S buffer (j+1)&1 last held P_{j-1}: make sure PV_{j-1} has retired before overwriting it
+        if (j >= 1) mbar_wait(o_done, (uint32_t)((j - 1) & 1));
+        issue_s(j + 1);
+      }
+      mbar_wait(bf ? p_full1 : p_full0, ph);
+      mbar_wait(bf ? v_full1 : v_full0, ph);
+      tcgen05_fence_after();
+#pragma unroll
+      for (int k = 0; k < TC_BC / 16; ++k)
+        umma_bf16_ts(tO, tSb[bf] + (uint32_t)k * 8u, desc_mnmajor(sV[bf], k), idesc_o, (j | k) != 0 ? 1u : 0u);
+      umma_commit(bf ? v_empty1 : v_empty0);
+      umma_commit(o_done);
+    }
+  } else if (warp >= 2) {
+    const int quad = warp & 3;
+    const int c = (warp - 2) >> 2;
+    const int r = quad * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+    const int row = q0 + r;
+    const float sl2 = p.scale * kLog2e;
+    float m_used = -INFINITY, l_part = 0.f;
+    for (int j = 0; j < n_tiles; ++j) {
+      const int bf = j & 1;
+      const uint32_t ph = (uint32_t)((j >> 1) & 1);
+      mbar_wait(bf ? s_full1 : s_full0, ph);
+      tcgen05_fence_after();
+      const int c0 = j * TC_BC + c * 32;
+      const bool need_mask = (j * TC_BC + TC_BC > kv_len) || (p.causal && j * TC_BC + TC_BC - 1 > q0);
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tSb[bf] + lane_off + c * 32, v);
+      tmem_ld_wait();
+      float mx = -INFINITY;
+      if (need_mask) {
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          const int col = c0 + t;
+          const bool ok = (col < kv_len) && (!p.causal || col <= row);
+          const float x = ok ? __uint_as_float(v[t]) : -INFINITY;
+          v[t] = __float_as_uint(x);
+          mx = fmaxf(mx, x);
+        }
+      } else {
+#pragma unroll
+        for (int t = 0; t < 32; ++t) mx = fmaxf(mx, __uint_as_float(v[t]));
+      }
+      float* mrow = sMax + (j & 1) * 512;
+      mrow[c * 128 + r] = mx;
+      asm volatile("bar.sync 1, 512;" ::: "memory");   // all S loads done (P may alias) + maxima visible
+      mx = fmaxf(fmaxf(mrow[r], mrow[128 + r]), fmaxf(mrow[256 + r], mrow[384 + r])) * sl2;
+      const bool grow = (j > 0) && (mx > m_used + 8.f);
+      if (j == 0) m_used = mx;
+      if (__any_sync(0xffffffffu, grow)) {
+        mbar_wait(o_done, (uint32_t)((j - 1) & 1));
+        tcgen05_fence_after();
+        const float m_new = fmaxf(m_used, mx);
+        const float f = (m_new == -INFINITY) ? 1.f : fast_exp2(m_used - m_new);
+        l_part *= f;
+        m_used = m_new;
+        uint32_t o[32];
+        tmem_ld_32x32b_x32(tO + lane_off + c * 32, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int t = 0; t < 32; ++t) o[t] = __float_as_uint(__uint_as_float(o[t]) * f);
+        tmem_st_32x32b_x32(tO + lane_off + c * 32, o);
+      }
+      const float m_eff = (m_used == -INFINITY) ? 0.f : m_used;
+      uint32_t pk[16];
+#pragma unroll
+      for (int t = 0; t < 32; t += 2) {
+        const float e0 = fast_exp2(fmaf(__uint_as_float(v[t]), sl2, -m_eff));      // masked: exp2(-inf) = 0
+        const float e1 = fast_exp2(fmaf(__uint_as_float(v[t + 1]), sl2, -m_eff));
+        l_part += e0 + e1;
+        pk[t >> 1] = pack_bf16x2(e0, e1);
+      }
+      tmem_st_32x32b_x16(tSb[bf] + lane_off + c * 16, pk);
+      tmem_st_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bf ? p_full1 : p_full0);
+    }
+    // epilogue: combine the four partial row sums, normalise, store
+    sSum[c * 128 + r] = l_part;
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+    const float l_sum = sSum[r] + sSum[128 + r] + sSum[256 + r] + sSum[384 + r];
+    float inv = 0.f;
+    uint32_t o[32];
+    if (n_tiles > 0) {
+      mbar_wait(o_done, (uint32_t)((n_tiles - 1) & 1));
+      tcgen05_fence_after();
+      inv = l_sum > 0.f ? 1.f / l_sum : 0.f;
+      tmem_ld_32x32b_x32(tO + lane_off + c * 32, o);
+      tmem_ld_wait();
+    } else {
+#pragma unroll
+      for (int t = 0; t < 32; ++t) o[t] = 0u;
+    }
+    if (row < p.T) {
+      bf16* orow = p.o + (long long)(tok0 + row) * p.ldo + (long long)h * TC_D + c * 32;
+#pragma unroll
+      for (int t = 0; t < 32; t += 8) {
+        int4 w;
+        w.x = pack_bf16x2(__uint_as_float(o[t]) * inv, __uint_as_float(o[t + 1]) * inv);
+        w.y = pack_bf16x2(__uint_as_float(o[t + 2]) * inv, __uint_as_float(o[t + 3]) * inv);
+        w.z = pack_bf16x2(__uint_as_float(o[t + 4]) * inv, __uint_as_float(o[t + 5]) * inv);
+        w.w = pack_bf16x2(__uint_as_float(o[t + 6]) * inv, __uint_as_float(o[t + 7]) * inv);
+        *reinterpret_cast<int4*>(orow + t) = w;
+      }
+      if (c == 0 && p.lse != nullptr)
+        p.lse[((long long)b * p.Hq + h) * p.T + row] = l_sum > 0.f ? (m_used + log2f(l_sum)) / kLog2e : -INFINITY;
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tcgen05_fence_after();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                     CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -354,7 +579,18 @@ MM_API int mm_attn_fwd_tc(const void* q, const void* k, const void* v, void* o, 
   p.o = (bf16*)o; p.lse = lse; p.seqlens = seqlens; p.ldo = ldo;
   p.B = B; p.T = T; p.Hq = Hq; p.Hkv = Hkv; p.scale = scale; p.causal = causal;
   dim3 grid((T + TC_BR - 1) / TC_BR, Hq, B);
-  flash_fwd_tc_kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(tq, tk, tv, p);
+  static const bool use_v1 = getenv("MM_ATTN_FWD_V1") != nullptr;
+  if (use_v1) {
+    flash_fwd_tc_kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(tq, tk, tv, p);
+  } else {
+    static std::once_flag once2;
+    static cudaError_t err2 = cudaSuccess;
+    std::call_once(once2, [&] {
+      err2 = cudaFuncSetAttribute(flash_fwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM);
+    });
+    MM_CHECK_CUDA(err2);
+    flash_fwd_tc2_kernel<<<grid, TC2_THREADS, TC2_SMEM, stream>>>(tq, tk, tv, p);
+  }
   MM_CHECK_LAUNCH();
   return MM_OK;
 }
@@ -392,11 +628,6 @@ struct TcBwdParams {
   int dbg;  // timing experiments only (MM_ATTN_DBG): 1 skip dQ reds, 2 skip dS smem stores, 4 skip exp2, 8 skip MMA drain
 };
 
-__device__ __forceinline__ float fast_exp2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
                : "memory");

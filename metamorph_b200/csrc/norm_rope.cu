@@ -60,13 +60,16 @@ rmsnorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16*
 }
 
 // ---------------------------------------------------------------------------------- RMSNorm bwd
-// dx = dres_in + rstd * (dy*w - xhat * mean(dy*w*xhat));  dw += sum_rows dy * xhat  (fp32 atomics)
+// dx = dres_in + rstd*dy*w - x * rstd^3 * sum(dy*w*x)/H ;  dw += sum_rows dy * x * rstd  (fp32 atomics)
+// Both row statistics (sum x^2 and sum dy*w*x) come from ONE pass and ONE block reduction per row
+// (double-buffered smem scratch -> a single __syncthreads per row).
 __global__ void __launch_bounds__(kNormThreads)
 rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                    const bf16* __restrict__ w, const bf16* __restrict__ dres_in,
                    bf16* __restrict__ dx, float* __restrict__ dw_accum, int M, int H, float eps) {
-  __shared__ float red[32];
+  __shared__ float red[2][2][kNormThreads / 32];
   const int nvec = H >> 3;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float dwp[kMaxVec][8];
   float wv[kMaxVec][8];
 #pragma unroll
@@ -78,17 +81,18 @@ rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
       wv[i][j] = (v < nvec) ? __bfloat162float(w[v * 8 + j]) : 0.f;
     }
   }
-  for (int row = blockIdx.x; row < M; row += gridDim.x) {
+  int par = 0;
+  for (int row = blockIdx.x; row < M; row += gridDim.x, par ^= 1) {
     const bf16* xr = x + (size_t)row * H;
     const bf16* dyr = dy + (size_t)row * H;
     float xv[kMaxVec][8], gv[kMaxVec][8];
-    float ss = 0.f;
+    float ss = 0.f, gwx = 0.f;
 #pragma unroll
     for (int i = 0; i < kMaxVec; ++i) {
       const int v = threadIdx.x + i * kNormThreads;
       if (v < nvec) {
-        const int4 rx = *reinterpret_cast<const int4*>(xr + v * 8);
-        const int4 rg = *reinterpret_cast<const int4*>(dyr + v * 8);
+        const int4 rx = ld_nc_int4(xr + v * 8);
+        const int4 rg = ld_nc_int4(dyr + v * 8);
         const uint32_t ux[4] = {(uint32_t)rx.x, (uint32_t)rx.y, (uint32_t)rx.z, (uint32_t)rx.w};
         const uint32_t ug[4] = {(uint32_t)rg.x, (uint32_t)rg.y, (uint32_t)rg.z, (uint32_t)rg.w};
 #pragma unroll
@@ -98,27 +102,19 @@ rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
           xv[i][2 * j] = f.x; xv[i][2 * j + 1] = f.y;
           gv[i][2 * j] = g.x; gv[i][2 * j + 1] = g.y;
           ss += f.x * f.x + f.y * f.y;
+          gwx += g.x * wv[i][2 * j] * f.x + g.y * wv[i][2 * j + 1] * f.y;
         }
       }
     }
-    ss = block_sum(ss, red);
-    const float rstd = rsqrtf(ss / (float)H + eps);
-    float dot = 0.f;
+    ss = warp_sum(ss);
+    gwx = warp_sum(gwx);
+    if (lane == 0) { red[par][0][warp] = ss; red[par][1][warp] = gwx; }
+    __syncthreads();
+    float tss = 0.f, tg = 0.f;
 #pragma unroll
-    for (int i = 0; i < kMaxVec; ++i) {
-      const int v = threadIdx.x + i * kNormThreads;
-      if (v < nvec) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float xhat = xv[i][j] * rstd;
-          dwp[i][j] += gv[i][j] * xhat;
-          gv[i][j] *= wv[i][j];       // dxhat
-          dot += gv[i][j] * xhat;
-          xv[i][j] = xhat;
-        }
-      }
-    }
-    dot = block_sum(dot, red) / (float)H;
+    for (int k = 0; k < kNormThreads / 32; ++k) { tss += red[par][0][k]; tg += red[par][1][k]; }
+    const float rstd = rsqrtf(tss / (float)H + eps);
+    const float coef = rstd * rstd * rstd * tg / (float)H;
     bf16* dxr = dx + (size_t)row * H;
 #pragma unroll
     for (int i = 0; i < kMaxVec; ++i) {
@@ -126,9 +122,12 @@ rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
       if (v < nvec) {
         float o[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = rstd * (gv[i][j] - xv[i][j] * dot);
+        for (int j = 0; j < 8; ++j) {
+          o[j] = rstd * gv[i][j] * wv[i][j] - xv[i][j] * coef;
+          dwp[i][j] += gv[i][j] * xv[i][j] * rstd;
+        }
         if (dres_in != nullptr) {
-          const int4 rr = *reinterpret_cast<const int4*>(dres_in + (size_t)row * H + v * 8);
+          const int4 rr = ld_nc_int4(dres_in + (size_t)row * H + v * 8);
           const uint32_t ur[4] = {(uint32_t)rr.x, (uint32_t)rr.y, (uint32_t)rr.z, (uint32_t)rr.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -269,7 +268,7 @@ MM_API int mm_rmsnorm_bwd(const void* dy, const void* x, const void* w, const vo
                           float* dw_accum, long long M, long long H, float eps, cudaStream_t stream) {
   MM_CHECK_ARG(M > 0 && H > 0 && H % 8 == 0 && H <= 8 * kNormThreads * kMaxVec,
                "mm_rmsnorm_bwd: need H%%8==0 and H<=%d (H=%lld)", 8 * kNormThreads * kMaxVec, H);
-  const int cap = mm_num_sms() * 4;
+  const int cap = mm_num_sms() * 8;
   const int grid = M < cap ? (int)M : cap;
   rmsnorm_bwd_kernel<<<grid, kNormThreads, 0, stream>>>((const bf16*)dy, (const bf16*)x,
                                                         (const bf16*)w, (const bf16*)dres_in,

@@ -68,7 +68,7 @@ class TrainingArguments:
     logging_steps: int = field(default=1)
     seed: int = field(default=42)
     gradient_checkpointing: bool = field(default=True)  # accepted for CLI compatibility; selective recompute is built in
-    save_gu_layers: int = field(default=16)
+    save_gu_layers: int = field(default=32)
 
 
 def rank0_print(*args):
