@@ -163,7 +163,9 @@ def decode_bench(model, dev, peaks, batch=8, prompt_len=128, new_positions=512):
         e1.record()
         torch.cuda.synchronize()
         times.append(e0.elapsed_time(e1))
-    ms = min(times)
+    total_ms = min(times)
+    tim = model._decode.last_timing
+    ms = tim["decode_ms"]                    # the 512 decode steps (device time), prefill/capture excluded
     n_vis = sum(int(x.shape[0]) for x in imgs)
     n_txt = sum(int(x.numel()) for x in ids)
     steps = new_positions
@@ -178,7 +180,10 @@ def decode_bench(model, dev, peaks, batch=8, prompt_len=128, new_positions=512):
             "visual_embeddings": n_vis, "text_tokens": n_txt, "prompt_len": prompt_len,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                          "bytes_per_step": bytes_total / steps},
-            "includes": "prefill of the 128-token prompts + CUDA-graph capture of the step"}
+            "total_ms_incl_prefill_and_graph_capture": total_ms, "graph_capture_ms": tim["capture_ms"],
+            "cuda_graph": tim["cuda_graph"],
+            "timed": "CUDA events around the 512 decode steps (prefill of the 8x128-token prompts and the one-off "
+                     "graph capture are reported separately)"}
 
 
 def run_reference_impl(args):

@@ -81,7 +81,9 @@ int mm_ce_fwd_bwd(const float* logits, long long ld, const int* labels, void* dl
                   cudaStream_t s);
 int mm_cosine_loss(const void* pred, const void* target, void* pred_norm, void* dpred, float* loss_sum,
                    long long R, int C, float grad_scale, cudaStream_t s);
-int mm_argmax_rows(const float* logits, long long ld, long long R, int V, int* out, cudaStream_t s);
+long long mm_argmax_workspace_bytes(long long R);
+int mm_argmax_rows(const float* logits, long long ld, long long R, int V, int* out, void* workspace,
+                   long long workspace_bytes, cudaStream_t s);
 
 /* torch.optim.AdamW step (train.py:82 --optim adamw_torch), fused over flat buffers; clip coefficient. */
 int mm_adamw_step(void* p16, float* p32, float* m, float* v, const void* grad, int grad_f32, long long n, float lr,
@@ -95,6 +97,15 @@ int mm_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse
                 long long ldq, long long ldk, long long ldv, long long ldo, int B, int T, int Hq, int Hkv,
                 int head_dim, int causal, float scale, cudaStream_t s);
 long long mm_attn_bwd_workspace_bytes(int B, int T, int Hq);
+/* tcgen05 / TMEM / TMA flash attention for head_dim 128 (csrc/attention_tc.cu); same contracts as above. */
+int mm_attn_fwd_tc(const void* q, const void* k, const void* v, void* o, float* lse, const int* seqlens,
+                   long long ldq, long long ldk, long long ldv, long long ldo, int B, int T, int Hq, int Hkv,
+                   int head_dim, int causal, float scale, cudaStream_t s);
+int mm_attn_bwd_tc(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse,
+                   void* dq, void* dk, void* dv, const int* seqlens, long long ldq, long long ldk, long long ldv,
+                   long long ldo, long long lddo, long long lddq, long long lddk, long long lddv, int B, int T,
+                   int Hq, int Hkv, int head_dim, float scale, void* workspace, long long workspace_bytes,
+                   cudaStream_t s);
 int mm_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse,
                 void* dq, void* dk, void* dv, const int* seqlens, long long ldq, long long ldk, long long ldv,
                 long long ldo, long long lddo, long long lddq, long long lddk, long long lddv, int B, int T,
@@ -105,9 +116,11 @@ int mm_attn_bwd(const void* q, const void* k, const void* v, const void* o, cons
 int mm_skinny_gemm(const void* x, const void* W, void* y, const void* bias, const void* resid, long long ldx,
                    long long ldw, long long ldy, long long ldr, int m, int N, int K, int epilogue, int out_f32,
                    cudaStream_t s);
+long long mm_decode_attn_workspace_bytes(int B, int Hq, int Hkv, int splits);
 int mm_decode_attn(const void* qkv, long long ldqkv, void* kcache, void* vcache, const int* pos,
                    const float* cos_t, const float* sin_t, void* out, long long ldo, int B, int Hq, int Hkv,
-                   int head_dim, int Tmax, float scale, cudaStream_t s);
+                   int head_dim, int Tmax, float scale, void* workspace, long long workspace_bytes, int splits,
+                   cudaStream_t s);
 int mm_kv_prefill(const void* qkv, long long ld, void* kcache, void* vcache, int B, int T, int Hq, int Hkv,
                   int head_dim, int Tmax, cudaStream_t s);
 int mm_decode_state_step(int* in_image_mode, int* total_image_tokens, int* total_output, int* finished, int* pos,

@@ -115,117 +115,194 @@ skinny_gemm_kernel(const bf16* __restrict__ x, long long ldx, const bf16* __rest
 }
 
 // ---------------------------------------------------------------------------------------------
-// decode attention. qkv: [B, (Hq+2Hkv)*128] (pre-RoPE) ; cache K/V: [B, Hkv, Tmax, 128]
-// grid (Hkv, B), 128 threads. pos[b] = index of the new token (= number of cached tokens).
-constexpr int DA_THREADS = 128;
+// decode attention (split-context). qkv: [B, (Hq+2Hkv)*128] (pre-RoPE); cache K/V: [B, Hkv, Tmax, 128].
+// grid (Hkv, B, S): every CTA handles 1/S of the cached positions of one (sequence, kv head) for the G
+// query heads of the group and writes partial (max, sum, unnormalised output); decode_attn_combine merges
+// the S partials. pos[b] = index of the new token; the CTA owning that position applies RoPE to the new k,
+// appends k/v to the cache and uses its on-chip copies (no cross-CTA read-after-write).
+constexpr int DA_THREADS = 256;
 constexpr int DA_D = 128;
 
+template <int G>
 __global__ void __launch_bounds__(DA_THREADS)
 decode_attn_kernel(const bf16* __restrict__ qkv, long long ldqkv, bf16* __restrict__ kc,
                    bf16* __restrict__ vc, const int* __restrict__ pos_arr,
                    const float* __restrict__ cos_t, const float* __restrict__ sin_t,
-                   bf16* __restrict__ out, long long ldo, int Hq, int Hkv, int Tmax, float scale) {
+                   float* __restrict__ part, int Hq, int Hkv, int Tmax, int S, float scale) {
   extern __shared__ float sm[];
-  const int G = Hq / Hkv;               // q heads per kv head (<= 8)
-  float* sq = sm;                        // [G][128]
-  float* sscore = sq + G * DA_D;         // [G][Tpad]
-  const int hk = blockIdx.x, b = blockIdx.y;
+  float* sq = sm;                          // [G][128] rotated, scaled q
+  float* sknew = sq + G * DA_D;            // [128] rotated new k
+  float* svnew = sknew + DA_D;             // [128] new v
+  float* sred = svnew + DA_D;              // [8 warps][G][128] partial outputs
+  float* sscore = sred + 8 * G * DA_D;     // [G][chunk_pad]
+  const int hk = blockIdx.x, b = blockIdx.y, sp = blockIdx.z;
   const int pos = pos_arr[b];
   const int n_ctx = pos + 1;
-  const int Tpad = (Tmax + 3) & ~3;
-  float* sred = sscore + G * Tpad;       // [G][4 warps][128] partial outputs
+  const int chunk = (n_ctx + S - 1) / S;
+  const int p0 = sp * chunk, p1 = min(n_ctx, p0 + chunk);
+  const int cpad = ((Tmax + S - 1) / S + 4) & ~3;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bf16* row = qkv + (long long)b * ldqkv;
   bf16* kcb = kc + ((long long)b * Hkv + hk) * Tmax * DA_D;
   bf16* vcb = vc + ((long long)b * Hkv + hk) * Tmax * DA_D;
   const float* cp = cos_t + (long long)pos * (DA_D / 2);
-  const float* sp = sin_t + (long long)pos * (DA_D / 2);
-  // RoPE on q heads -> smem (fp32, pre-scaled), on k -> cache; v -> cache
+  const float* sp_ = sin_t + (long long)pos * (DA_D / 2);
+  const bool owns_new = (pos >= p0 && pos < p1);
   for (int i = tid; i < G * (DA_D / 2); i += DA_THREADS) {
     const int h = i / (DA_D / 2), j = i % (DA_D / 2);
     const bf16* qh = row + (long long)(hk * G + h) * DA_D;
     const float a = __bfloat162float(qh[j]), c = __bfloat162float(qh[j + DA_D / 2]);
     // bf16 rounding of the rotated q mirrors the training kernel (rope_ writes bf16)
-    sq[h * DA_D + j] = __bfloat162float(__float2bfloat16(a * cp[j] - c * sp[j])) * scale;
-    sq[h * DA_D + j + DA_D / 2] = __bfloat162float(__float2bfloat16(c * cp[j] + a * sp[j])) * scale;
+    sq[h * DA_D + j] = __bfloat162float(__float2bfloat16(a * cp[j] - c * sp_[j])) * scale;
+    sq[h * DA_D + j + DA_D / 2] = __bfloat162float(__float2bfloat16(c * cp[j] + a * sp_[j])) * scale;
   }
-  if (tid < DA_D / 2) {
+  if (owns_new && tid < DA_D / 2) {
     const bf16* kh = row + (long long)(Hq + hk) * DA_D;
-    const float a = __bfloat162float(kh[tid]), c = __bfloat162float(kh[tid + DA_D / 2]);
-    kcb[(long long)pos * DA_D + tid] = __float2bfloat16(a * cp[tid] - c * sp[tid]);
-    kcb[(long long)pos * DA_D + tid + DA_D / 2] = __float2bfloat16(c * cp[tid] + a * sp[tid]);
-  } else {
-    const int j = (tid - DA_D / 2) * 2;
     const bf16* vh = row + (long long)(Hq + Hkv + hk) * DA_D;
-    vcb[(long long)pos * DA_D + j] = vh[j];
-    vcb[(long long)pos * DA_D + j + 1] = vh[j + 1];
+    const float a = __bfloat162float(kh[tid]), c = __bfloat162float(kh[tid + DA_D / 2]);
+    const bf16 k0 = __float2bfloat16(a * cp[tid] - c * sp_[tid]);
+    const bf16 k1 = __float2bfloat16(c * cp[tid] + a * sp_[tid]);
+    kcb[(long long)pos * DA_D + tid] = k0;
+    kcb[(long long)pos * DA_D + tid + DA_D / 2] = k1;
+    sknew[tid] = __bfloat162float(k0);
+    sknew[tid + DA_D / 2] = __bfloat162float(k1);
+    const bf16 v0 = vh[2 * tid], v1 = vh[2 * tid + 1];
+    vcb[(long long)pos * DA_D + 2 * tid] = v0;
+    vcb[(long long)pos * DA_D + 2 * tid + 1] = v1;
+    svnew[2 * tid] = __bfloat162float(v0);
+    svnew[2 * tid + 1] = __bfloat162float(v1);
   }
   __syncthreads();
-  // scores: one thread per cached position
-  for (int p = tid; p < n_ctx; p += DA_THREADS) {
-    const int4* kp = reinterpret_cast<const int4*>(kcb + (long long)p * DA_D);
-    float s[8];
+  // ---- scores: one thread per cached position of this split
+  for (int p = p0 + tid; p < p1; p += DA_THREADS) {
+    float s[G];
 #pragma unroll
-    for (int h = 0; h < 8; ++h) s[h] = 0.f;
-#pragma unroll 4
-    for (int v = 0; v < DA_D / 8; ++v) {
-      const int4 raw = kp[v];
-      const uint32_t u[4] = {(uint32_t)raw.x, (uint32_t)raw.y, (uint32_t)raw.z, (uint32_t)raw.w};
-      float kf[8];
+    for (int h = 0; h < G; ++h) s[h] = 0.f;
+    if (p == pos) {
+      for (int d = 0; d < DA_D; ++d) {
+        const float kf = sknew[d];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = unpack_bf16x2(u[j]);
-        kf[2 * j] = f.x;
-        kf[2 * j + 1] = f.y;
+        for (int h = 0; h < G; ++h) s[h] += sq[h * DA_D + d] * kf;
       }
-      for (int h = 0; h < G; ++h) {
-        const float* qh = sq + h * DA_D + v * 8;
+    } else {
+      const int4* kp = reinterpret_cast<const int4*>(kcb + (long long)p * DA_D);
+#pragma unroll 4
+      for (int v = 0; v < DA_D / 8; ++v) {
+        const int4 raw = kp[v];
+        const uint32_t u[4] = {(uint32_t)raw.x, (uint32_t)raw.y, (uint32_t)raw.z, (uint32_t)raw.w};
+        float kf[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) s[h] += qh[j] * kf[j];
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack_bf16x2(u[j]);
+          kf[2 * j] = f.x;
+          kf[2 * j + 1] = f.y;
+        }
+#pragma unroll
+        for (int h = 0; h < G; ++h) {
+          const float4 q0 = *reinterpret_cast<const float4*>(sq + h * DA_D + v * 8);
+          const float4 q1 = *reinterpret_cast<const float4*>(sq + h * DA_D + v * 8 + 4);
+          s[h] += q0.x * kf[0] + q0.y * kf[1] + q0.z * kf[2] + q0.w * kf[3] + q1.x * kf[4] + q1.y * kf[5] +
+                  q1.z * kf[6] + q1.w * kf[7];
+        }
       }
     }
-    for (int h = 0; h < G; ++h) sscore[h * Tpad + p] = s[h];
+#pragma unroll
+    for (int h = 0; h < G; ++h) sscore[h * cpad + (p - p0)] = s[h];
   }
   __syncthreads();
-  // softmax per head (warp h handles head h, h+4, ...)
+  // ---- local softmax statistics per head (warp h handles heads h, h+8, ...)
+  __shared__ float s_m[8], s_l[8];
+  const int n_loc = max(p1 - p0, 0);
   for (int h = warp; h < G; h += DA_THREADS / 32) {
     float mx = -INFINITY;
-    for (int p = lane; p < n_ctx; p += 32) mx = fmaxf(mx, sscore[h * Tpad + p]);
+    for (int i = lane; i < n_loc; i += 32) mx = fmaxf(mx, sscore[h * cpad + i]);
     mx = warp_max(mx);
     float sum = 0.f;
-    for (int p = lane; p < n_ctx; p += 32) {
-      const float e = __expf(sscore[h * Tpad + p] - mx);
-      sscore[h * Tpad + p] = e;
+    for (int i = lane; i < n_loc; i += 32) {
+      const float e = __expf(sscore[h * cpad + i] - mx);
+      sscore[h * cpad + i] = e;
       sum += e;
     }
     sum = warp_sum(sum);
-    const float inv = 1.f / sum;
-    for (int p = lane; p < n_ctx; p += 32) sscore[h * Tpad + p] *= inv;
+    if (lane == 0) { s_m[h] = mx; s_l[h] = sum; }
   }
   __syncthreads();
-  // O = P V: lane owns 4 dims, warp w takes positions w, w+4, ...
-  float o[8][4];
+  // ---- O_partial = P V: lane owns 4 dims, warp w takes positions p0+w, p0+w+8, ... (4 loads in flight)
+  float o[G][4];
 #pragma unroll
-  for (int h = 0; h < 8; ++h)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) o[h][j] = 0.f;
-  for (int p = warp; p < n_ctx; p += DA_THREADS / 32) {
-    const uint2 raw = *reinterpret_cast<const uint2*>(vcb + (long long)p * DA_D + lane * 4);
-    const float2 f0 = unpack_bf16x2(raw.x), f1 = unpack_bf16x2(raw.y);
-    for (int h = 0; h < G; ++h) {
-      const float pr = sscore[h * Tpad + p];
-      o[h][0] += pr * f0.x; o[h][1] += pr * f0.y; o[h][2] += pr * f1.x; o[h][3] += pr * f1.y;
-    }
-  }
   for (int h = 0; h < G; ++h)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) sred[(h * 4 + warp) * DA_D + lane * 4 + j] = o[h][j];
+    for (int j = 0; j < 4; ++j) o[h][j] = 0.f;
+  for (int i0 = warp; i0 < n_loc; i0 += 4 * (DA_THREADS / 32)) {
+    float vf[4][4];
+    int idx[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      idx[u] = i0 + u * (DA_THREADS / 32);
+      const int p = p0 + idx[u];
+      if (idx[u] < n_loc) {
+        if (p == pos) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) vf[u][j] = svnew[lane * 4 + j];
+        } else {
+          const uint2 raw = *reinterpret_cast<const uint2*>(vcb + (long long)p * DA_D + lane * 4);
+          const float2 f0 = unpack_bf16x2(raw.x), f1 = unpack_bf16x2(raw.y);
+          vf[u][0] = f0.x; vf[u][1] = f0.y; vf[u][2] = f1.x; vf[u][3] = f1.y;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) vf[u][j] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (idx[u] < n_loc) {
+#pragma unroll
+        for (int h = 0; h < G; ++h) {
+          const float pr = sscore[h * cpad + idx[u]];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[h][j] += pr * vf[u][j];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < G; ++h)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sred[(warp * G + h) * DA_D + lane * 4 + j] = o[h][j];
   __syncthreads();
+  // partial layout: [B, Hkv, S, G, 2 + 128]
+  float* pout = part + (((long long)b * Hkv + hk) * S + sp) * G * (2 + DA_D);
   for (int i = tid; i < G * DA_D; i += DA_THREADS) {
     const int h = i / DA_D, dcol = i % DA_D;
-    const float s = sred[(h * 4 + 0) * DA_D + dcol] + sred[(h * 4 + 1) * DA_D + dcol] +
-                    sred[(h * 4 + 2) * DA_D + dcol] + sred[(h * 4 + 3) * DA_D + dcol];
-    out[(long long)b * ldo + (long long)(hk * G + h) * DA_D + dcol] = __float2bfloat16(s);
+    float acc = 0.f;
+#pragma unroll
+    for (int w = 0; w < DA_THREADS / 32; ++w) acc += sred[(w * G + h) * DA_D + dcol];
+    pout[h * (2 + DA_D) + 2 + dcol] = acc;
+  }
+  if (tid < G) {
+    pout[tid * (2 + DA_D)] = n_loc > 0 ? s_m[tid] : -INFINITY;
+    pout[tid * (2 + DA_D) + 1] = n_loc > 0 ? s_l[tid] : 0.f;
+  }
+}
+
+// out[b, (hk*G+h)*128 + d] = sum_s o_s e^{m_s - M} / sum_s l_s e^{m_s - M}
+__global__ void decode_attn_combine_kernel(const float* __restrict__ part, bf16* __restrict__ out,
+                                           long long ldo, int Hkv, int G, int S) {
+  const int hk = blockIdx.x, b = blockIdx.y;
+  const float* pin = part + (((long long)b * Hkv + hk) * S) * G * (2 + DA_D);
+  for (int i = threadIdx.x; i < G * DA_D; i += blockDim.x) {
+    const int h = i / DA_D, dcol = i % DA_D;
+    float M = -INFINITY;
+    for (int s = 0; s < S; ++s) M = fmaxf(M, pin[(s * G + h) * (2 + DA_D)]);
+    float L = 0.f, acc = 0.f;
+    for (int s = 0; s < S; ++s) {
+      const float* ps = pin + (s * G + h) * (2 + DA_D);
+      const float w = (ps[0] == -INFINITY) ? 0.f : __expf(ps[0] - M);
+      L += ps[1] * w;
+      acc += ps[2 + dcol] * w;
+    }
+    out[(long long)b * ldo + (long long)(hk * G + h) * DA_D + dcol] = __float2bfloat16(acc / L);
   }
 }
 
@@ -362,19 +439,41 @@ MM_API int mm_skinny_gemm(const void* x, const void* W, void* y, const void* bia
   return MM_OK;
 }
 
+MM_API long long mm_decode_attn_workspace_bytes(int B, int Hq, int Hkv, int splits) {
+  return (long long)B * Hkv * splits * (Hq / Hkv) * (2 + DA_D) * 4;
+}
+
 MM_API int mm_decode_attn(const void* qkv, long long ldqkv, void* kcache, void* vcache, const int* pos,
                           const float* cos_t, const float* sin_t, void* out, long long ldo, int B,
-                          int Hq, int Hkv, int head_dim, int Tmax, float scale, cudaStream_t stream) {
-  MM_CHECK_ARG(head_dim == DA_D && Hq % Hkv == 0 && Hq / Hkv <= 8, "mm_decode_attn: need head_dim 128, group<=8");
+                          int Hq, int Hkv, int head_dim, int Tmax, float scale, void* workspace,
+                          long long workspace_bytes, int splits, cudaStream_t stream) {
+  MM_CHECK_ARG(head_dim == DA_D && Hq % Hkv == 0, "mm_decode_attn: need head_dim 128");
   const int G = Hq / Hkv;
-  const int Tpad = (Tmax + 3) & ~3;
-  const size_t smem = (size_t)(G * DA_D + G * Tpad + G * 4 * DA_D) * sizeof(float);
-  MM_CHECK_ARG(smem <= 200 * 1024, "mm_decode_attn: Tmax %d too large for the single-pass kernel", Tmax);
-  if (smem > 48 * 1024)
-    MM_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  decode_attn_kernel<<<dim3(Hkv, B), DA_THREADS, smem, stream>>>(
-      (const bf16*)qkv, ldqkv, (bf16*)kcache, (bf16*)vcache, pos, cos_t, sin_t, (bf16*)out, ldo, Hq, Hkv,
-      Tmax, scale);
+  MM_CHECK_ARG(G == 1 || G == 2 || G == 4 || G == 8, "mm_decode_attn: GQA group must be 1, 2, 4 or 8");
+  MM_CHECK_ARG(splits >= 1 && splits <= 64, "mm_decode_attn: splits in [1,64]");
+  MM_CHECK_ARG(workspace != nullptr && workspace_bytes >= mm_decode_attn_workspace_bytes(B, Hq, Hkv, splits),
+               "mm_decode_attn: workspace too small");
+  const int cpad = ((Tmax + splits - 1) / splits + 4) & ~3;
+  const size_t smem = (size_t)(G * DA_D + 2 * DA_D + 8 * G * DA_D + G * cpad) * sizeof(float);
+  MM_CHECK_ARG(smem <= 200 * 1024, "mm_decode_attn: Tmax/splits = %d positions per CTA is too large", cpad);
+  dim3 grid(Hkv, B, splits);
+#define MM_DA_LAUNCH(GG)                                                                                     \
+  do {                                                                                                       \
+    if (smem > 48 * 1024)                                                                                    \
+      MM_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         (int)smem));                                                        \
+    decode_attn_kernel<GG><<<grid, DA_THREADS, smem, stream>>>(                                              \
+        (const bf16*)qkv, ldqkv, (bf16*)kcache, (bf16*)vcache, pos, cos_t, sin_t, (float*)workspace, Hq, Hkv, \
+        Tmax, splits, scale);                                                                                \
+  } while (0)
+  if (G == 1) MM_DA_LAUNCH(1);
+  else if (G == 2) MM_DA_LAUNCH(2);
+  else if (G == 4) MM_DA_LAUNCH(4);
+  else MM_DA_LAUNCH(8);
+#undef MM_DA_LAUNCH
+  MM_CHECK_LAUNCH();
+  decode_attn_combine_kernel<<<dim3(Hkv, B), 128, 0, stream>>>((const float*)workspace, (bf16*)out, ldo, Hkv, G,
+                                                               splits);
   MM_CHECK_LAUNCH();
   return MM_OK;
 }

@@ -24,7 +24,6 @@ constexpr int BM = 128;
 constexpr int BK = 64;       // 64 bf16 = 128 bytes = one swizzle-128B row
 constexpr int UMMA_K = 16;
 constexpr int kThreads = 256;
-constexpr int GROUP_M = 16;  // rasterisation group (tiles sharing B columns stay L2-resident)
 
 enum Epilogue : int {
   EPI_STORE = 0,           // C = acc
@@ -71,7 +70,7 @@ __device__ __forceinline__ uint64_t make_desc_base(bool mn_major) {
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                    const __grid_constant__ CUtensorMap tmap_b, int M, int N, int K,
+                    const __grid_constant__ CUtensorMap tmap_b, int M, int N, int K, int group_m,
                     EpiParams ep) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -112,10 +111,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   auto tile_coords = [&](int t, int& m_blk, int& n_blk) {
-    const int per_group = GROUP_M * num_n;
+    // rasterisation: a group of `group_m` row-blocks (its A panel sized to stay L2-resident) sweeps all
+    // column-blocks, so A is read from HBM once and B once per group
+    const int per_group = group_m * num_n;
     const int g = t / per_group;
-    const int first_m = g * GROUP_M;
-    const int gsz = min(GROUP_M, num_m - first_m);
+    const int first_m = g * group_m;
+    const int gsz = min(group_m, num_m - first_m);
     const int r = t - g * per_group;
     m_blk = first_m + (r % gsz);
     n_blk = r / gsz;
@@ -399,7 +400,12 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, co
   MM_CHECK_CUDA(attr_err);
   const int num_tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = num_tiles < mm_num_sms() ? num_tiles : mm_num_sms();
-  kern<<<grid, kThreads, Cfg<BN>::kSmemBytes, stream>>>(ta, tb, M, N, K, ep);
+  // A panel of a group ~ 48 MB of the 126 MB L2 (measured: the 16-row-block default re-read B 8x from HBM
+  // on the gate/up GEMM: 2.98 GB of DRAM traffic for 1.31 GB algorithmic, profiles/r01_gemm_ncu_summary.json)
+  long long gm = (48ll << 20) / ((long long)BM * K * 2);
+  if (gm < 4) gm = 4;
+  if (gm > 64) gm = 64;
+  kern<<<grid, kThreads, Cfg<BN>::kSmemBytes, stream>>>(ta, tb, M, N, K, (int)gm, ep);
   MM_CHECK_LAUNCH();
   return MM_OK;
 }

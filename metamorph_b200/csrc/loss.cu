@@ -154,39 +154,52 @@ __global__ void cosine_loss_kernel(const bf16* __restrict__ pred, const bf16* __
   }
 }
 
-// argmax over V fp32 logits per row (first index wins ties, like torch.argmax on CUDA is not
-// guaranteed to, but deterministic here).
-__global__ void __launch_bounds__(512)
-argmax_rows_kernel(const float* __restrict__ logits, long long ld, int V, int* __restrict__ out) {
-  __shared__ float sval[16];
-  __shared__ int sidx[16];
-  const float* x = logits + (long long)blockIdx.x * ld;
+// argmax over V fp32 logits per row, two stages so that a handful of rows still fills the GPU:
+// stage 1: grid (R, kArgmaxSplits) partial (value, index) per slice; stage 2: one warp per row.
+// Ties resolve to the smallest index (deterministic).
+constexpr int kArgmaxSplits = 64;
+
+__device__ __forceinline__ void argmax_combine(float& best, int& bi, float ov, int oi) {
+  if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+}
+
+__global__ void __launch_bounds__(256)
+argmax_partial_kernel(const float* __restrict__ logits, long long ld, int V, float* __restrict__ pval,
+                      int* __restrict__ pidx) {
+  __shared__ float sval[8];
+  __shared__ int sidx[8];
+  const int r = blockIdx.x, sp = blockIdx.y;
+  const int per = (V + kArgmaxSplits - 1) / kArgmaxSplits;
+  const int j0 = sp * per, j1 = min(V, j0 + per);
+  const float* x = logits + (long long)r * ld;
   float best = -INFINITY;
   int bi = 0x7fffffff;
-  for (int j = threadIdx.x; j < V; j += blockDim.x) {
+  for (int j = j0 + threadIdx.x; j < j1; j += blockDim.x) {
     const float v = x[j];
     if (v > best) { best = v; bi = j; }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-  }
+  for (int o = 16; o > 0; o >>= 1)
+    argmax_combine(best, bi, __shfl_xor_sync(0xffffffffu, best, o), __shfl_xor_sync(0xffffffffu, bi, o));
   if ((threadIdx.x & 31) == 0) { sval[threadIdx.x >> 5] = best; sidx[threadIdx.x >> 5] = bi; }
   __syncthreads();
-  if (threadIdx.x < 32) {
-    const int nw = blockDim.x >> 5;
-    best = threadIdx.x < nw ? sval[threadIdx.x] : -INFINITY;
-    bi = threadIdx.x < nw ? sidx[threadIdx.x] : 0x7fffffff;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-    }
-    if (threadIdx.x == 0) out[blockIdx.x] = bi;
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) argmax_combine(best, bi, sval[w], sidx[w]);
+    pval[r * kArgmaxSplits + sp] = best;
+    pidx[r * kArgmaxSplits + sp] = bi;
   }
+}
+
+__global__ void argmax_final_kernel(const float* __restrict__ pval, const int* __restrict__ pidx,
+                                    int* __restrict__ out) {
+  const int r = blockIdx.x, lane = threadIdx.x;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int s = lane; s < kArgmaxSplits; s += 32) argmax_combine(best, bi, pval[r * kArgmaxSplits + s], pidx[r * kArgmaxSplits + s]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    argmax_combine(best, bi, __shfl_xor_sync(0xffffffffu, best, o), __shfl_xor_sync(0xffffffffu, bi, o));
+  if (lane == 0) out[r] = bi;
 }
 
 }  // namespace
@@ -216,10 +229,19 @@ MM_API int mm_cosine_loss(const void* pred, const void* target, void* pred_norm,
   return MM_OK;
 }
 
-MM_API int mm_argmax_rows(const float* logits, long long ld, long long R, int V, int* out,
-                          cudaStream_t stream) {
+// workspace: R * 64 floats followed by R * 64 ints (mm_argmax_workspace_bytes)
+MM_API long long mm_argmax_workspace_bytes(long long R) { return R * kArgmaxSplits * 8; }
+
+MM_API int mm_argmax_rows(const float* logits, long long ld, long long R, int V, int* out, void* workspace,
+                          long long workspace_bytes, cudaStream_t stream) {
   MM_CHECK_ARG(R > 0 && V > 0 && ld >= V, "mm_argmax_rows: bad shape");
-  argmax_rows_kernel<<<(unsigned)R, 512, 0, stream>>>(logits, ld, V, out);
+  MM_CHECK_ARG(workspace != nullptr && workspace_bytes >= mm_argmax_workspace_bytes(R),
+               "mm_argmax_rows: workspace too small");
+  float* pval = reinterpret_cast<float*>(workspace);
+  int* pidx = reinterpret_cast<int*>(pval + R * kArgmaxSplits);
+  argmax_partial_kernel<<<dim3((unsigned)R, kArgmaxSplits), 256, 0, stream>>>(logits, ld, V, pval, pidx);
+  MM_CHECK_LAUNCH();
+  argmax_final_kernel<<<(unsigned)R, 32, 0, stream>>>(pval, pidx, out);
   MM_CHECK_LAUNCH();
   return MM_OK;
 }

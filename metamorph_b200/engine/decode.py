@@ -97,6 +97,8 @@ class DecodeEngine:
             ops.decode_next_input(st["append_kind"], st["next_token"], model.embed_tokens.weight.data,
                                   prediction, xin)
 
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record()                                   # prefill done (enqueued) -> decode steps start
         heads_and_state(h_last, 0)
 
         def one_step_body():
@@ -120,6 +122,7 @@ class DecodeEngine:
         if self.use_cuda_graph and steps_cap > 2:
             heads_and_state(one_step_body(), 1)              # eager warm-up step (sets kernel attributes)
             step = 2
+            ev[1].record()
             try:
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
@@ -129,6 +132,10 @@ class DecodeEngine:
             except Exception:  # noqa: BLE001 - capture unsupported: stay on stream launches
                 graph = None
                 torch.cuda.synchronize()
+            ev[2].record()
+        else:
+            ev[1].record()
+            ev[2].record()
         while step < steps_cap:
             if step % poll_every == 0 and bool(st["finished"].all()):
                 break
@@ -138,10 +145,14 @@ class DecodeEngine:
                 heads_and_state(one_step_body(), step)
             step += 1
 
+        ev[3].record()
         n_ids = st["n_ids"].cpu().tolist()
         n_img = st["n_img"].cpu().tolist()
         ids_cpu = st["ids_out"]
         out_ids = [ids_cpu[b, :n_ids[b]].clone() for b in range(B)]
         out_img = [img_out[b, :n_img[b]].clone() for b in range(B)]
         self.last_steps = step
+        # device time of the decode steps (graph capture is a one-off host-side cost, reported separately)
+        self.last_timing = {"steps": step, "decode_ms": ev[0].elapsed_time(ev[1]) + ev[2].elapsed_time(ev[3]),
+                            "capture_ms": ev[1].elapsed_time(ev[2]), "cuda_graph": graph is not None}
         return out_ids, out_img

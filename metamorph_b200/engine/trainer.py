@@ -119,7 +119,9 @@ class TrainEngine:
             if p.requires_grad and "vision_tower" not in n and "vision_proj" not in n:
                 self.opt[n] = _OptState(p)
         self._state_by_ptr = {st.p16.data_ptr(): st for st in self.opt.values()}
-        self.comm_stream = torch.cuda.Stream() if self.world > 1 else None
+        # side stream: gradient all-reduce (N>1) and the HBM-bound fused AdamW run here, concurrently with
+        # the tensor-core-bound backward GEMMs of the next layers on the main stream
+        self.comm_stream = torch.cuda.Stream()
         self.provider = FusedGradProvider(model, self) if max_grad_norm is None else GradProvider(model)
         self.kernel_launch_estimate = 0
 
@@ -137,15 +139,13 @@ class TrainEngine:
     def reduce_and_apply(self, params, flat_buffers):
         """(all-reduce the bucket ->) fused AdamW. Returns an event marking bucket reuse safety."""
         lr = self.current_lr
-        if self.world == 1:
-            self._apply(params, lr, 1.0)
-            return None
         ready = torch.cuda.Event()
         ready.record()
         with torch.cuda.stream(self.comm_stream):
             self.comm_stream.wait_event(ready)
-            for b in flat_buffers:
-                dist.all_reduce(b, op=dist.ReduceOp.SUM)
+            if self.world > 1:
+                for b in flat_buffers:
+                    dist.all_reduce(b, op=dist.ReduceOp.SUM)
             self._apply(params, lr, 1.0 / self.world)
             done = torch.cuda.Event()
             done.record()

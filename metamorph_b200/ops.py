@@ -248,11 +248,24 @@ def cosine_loss(pred, target, loss_sum=None, pred_norm=None, dpred=None, grad_sc
          ll(pred.shape[0]), c_int(pred.shape[1]), c_float(grad_scale), stream_ptr())
 
 
+_ws_cache = {}
+
+
+def _workspace(key, nbytes, device):
+    buf = _ws_cache.get((key, str(device)))
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        _ws_cache[(key, str(device))] = buf
+    return buf
+
+
 def argmax_rows(logits_f32, V, out=None):
     require_cuda(logits_f32)
     R = logits_f32.shape[0]
     out = torch.empty((R,), dtype=torch.int32, device=logits_f32.device) if out is None else out
-    call("mm_argmax_rows", ptr(logits_f32), ll(logits_f32.stride(0)), ll(R), c_int(V), ptr(out), stream_ptr())
+    ws = _workspace("argmax", R * 64 * 8, logits_f32.device)
+    call("mm_argmax_rows", ptr(logits_f32), ll(logits_f32.stride(0)), ll(R), c_int(V), ptr(out), ptr(ws),
+         ll(ws.numel()), stream_ptr())
     return out
 
 
@@ -338,15 +351,18 @@ def skinny_gemm(x, w, *, bias=None, resid=None, epilogue=SK_STORE, out=None, out
     return out
 
 
-def decode_attn(qkv, kcache, vcache, pos, cos, sin, Hq, Hkv, head_dim, scale, out=None):
+def decode_attn(qkv, kcache, vcache, pos, cos, sin, Hq, Hkv, head_dim, scale, out=None, splits=None):
     require_cuda(qkv, kcache, vcache, pos, cos, sin)
     B = qkv.shape[0]
     Tmax = kcache.shape[2]
+    if splits is None:  # enough CTAs to cover the SMs: B*Hkv*splits >= ~2 x 148
+        splits = max(1, min(16, -(-296 // (B * Hkv))))
     if out is None:
         out = torch.empty((B, Hq * head_dim), dtype=torch.bfloat16, device=qkv.device)
+    ws = _workspace("decode_attn", B * Hkv * splits * (Hq // Hkv) * (2 + head_dim) * 4, qkv.device)
     call("mm_decode_attn", ptr(qkv), ll(qkv.stride(0)), ptr(kcache), ptr(vcache), ptr(pos), ptr(cos),
          ptr(sin), ptr(out), ll(out.stride(0)), c_int(B), c_int(Hq), c_int(Hkv), c_int(head_dim),
-         c_int(Tmax), c_float(scale), stream_ptr())
+         c_int(Tmax), c_float(scale), ptr(ws), ll(ws.numel()), c_int(splits), stream_ptr())
     return out
 
 

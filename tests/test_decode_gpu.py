@@ -1,0 +1,117 @@
+"""Decode kernels on B200 against torch fp32 restatements: skinny GEMM epilogues, split-context attention
+with RoPE + cache append, two-stage argmax, batched state machine vs the oracle loop."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _close(a, b, rel, what):
+    a, b = a.float(), b.float()
+    err = (a - b).abs().max().item()
+    scale = b.abs().max().item() + 1e-6
+    assert err <= rel * scale, f"{what}: max_err={err:.5f} scale={scale:.4f}"
+
+
+@pytest.mark.parametrize("m", [1, 5, 8])
+def test_skinny_gemm(cuda_device, m):
+    from metamorph_b200 import ops
+    from metamorph_b200.engine.packing import interleave_gate_up
+    torch.manual_seed(0)
+    K, N = 4096, 1184
+    x = torch.randn(m, K, device=cuda_device).bfloat16()
+    w = (torch.randn(N, K, device=cuda_device) * 0.03).bfloat16()
+    bias = torch.randn(N, device=cuda_device).bfloat16()
+    res = torch.randn(m, N, device=cuda_device).bfloat16()
+    base = x.float() @ w.float().t()
+    _close(ops.skinny_gemm(x, w), base, 1e-2, "store")
+    _close(ops.skinny_gemm(x, w, bias=bias, epilogue=ops.SK_BIAS), base + bias.float(), 1e-2, "bias")
+    _close(ops.skinny_gemm(x, w, bias=bias, epilogue=ops.SK_BIAS_GELU), F.gelu(base + bias.float()), 1e-2, "gelu")
+    _close(ops.skinny_gemm(x, w, resid=res, epilogue=ops.SK_RESID), base + res.float(), 1e-2, "resid")
+    out32 = torch.empty(m, N, device=cuda_device, dtype=torch.float32)
+    ops.skinny_gemm(x, w, out=out32)
+    _close(out32, base, 2e-3, "fp32 out")
+    wg = (torch.randn(512, K, device=cuda_device) * 0.03).bfloat16()
+    wu = (torch.randn(512, K, device=cuda_device) * 0.03).bfloat16()
+    act = ops.skinny_gemm(x, interleave_gate_up(wg, wu), epilogue=ops.SK_SWIGLU)
+    _close(act, F.silu(x.float() @ wg.float().t()) * (x.float() @ wu.float().t()), 1e-2, "swiglu")
+
+
+@pytest.mark.parametrize("splits", [1, 3, 5])
+def test_decode_attention_split_context(cuda_device, splits):
+    from metamorph_b200 import ops
+    torch.manual_seed(1)
+    B, Hq, Hkv, d, Tmax = 3, 8, 2, 128, 300
+    pos = torch.tensor([0, 57, 299], device=cuda_device, dtype=torch.int32)
+    kc = torch.randn(B, Hkv, Tmax, d, device=cuda_device).bfloat16()
+    vc = torch.randn(B, Hkv, Tmax, d, device=cuda_device).bfloat16()
+    qkv = torch.randn(B, (Hq + 2 * Hkv) * d, device=cuda_device).bfloat16()
+    inv = 1.0 / (500000.0 ** (torch.arange(0, d, 2, device=cuda_device).float() / d))
+    ang = torch.arange(Tmax + 1, device=cuda_device).float()[:, None] * inv[None]
+    cos, sin = ang.cos().contiguous(), ang.sin().contiguous()
+    kc0, vc0 = kc.clone(), vc.clone()
+    out = ops.decode_attn(qkv, kc, vc, pos, cos, sin, Hq, Hkv, d, 1 / math.sqrt(d), splits=splits)
+
+    def rope(x, p):
+        c, s = cos[p], sin[p]
+        x1, x2 = x[..., :d // 2], x[..., d // 2:]
+        return torch.cat([x1 * c - x2 * s, x2 * c + x1 * s], -1)
+
+    for b in range(B):
+        p = int(pos[b])
+        q = rope(qkv[b, :Hq * d].float().view(Hq, d), p).bfloat16().float()
+        kn = rope(qkv[b, Hq * d:(Hq + Hkv) * d].float().view(Hkv, d), p).bfloat16()
+        vn = qkv[b, (Hq + Hkv) * d:].view(Hkv, d)
+        assert torch.equal(kc[b, :, p], kn) and torch.equal(vc[b, :, p], vn), "new k/v must be appended"
+        assert torch.equal(kc[b, :, :p], kc0[b, :, :p]) and torch.equal(vc[b, :, p + 1:], vc0[b, :, p + 1:])
+        K = kc[b, :, :p + 1].float().repeat_interleave(Hq // Hkv, 0)
+        V = vc[b, :, :p + 1].float().repeat_interleave(Hq // Hkv, 0)
+        s = torch.einsum("hd,hpd->hp", q, K) / math.sqrt(d)
+        ref = torch.einsum("hp,hpd->hd", s.softmax(-1), V).reshape(-1)
+        _close(out[b], ref, 2e-2, f"decode attn b={b}")
+
+
+def test_argmax_two_stage(cuda_device):
+    from metamorph_b200 import ops
+    torch.manual_seed(2)
+    V, ld = 128258, 128264
+    buf = torch.randn(8, ld, device=cuda_device)
+    buf[3, 77] = 100.0
+    buf[3, 99999] = 100.0   # tie -> smallest index
+    assert ops.argmax_rows(buf, V).long().equal(buf[:, :V].argmax(-1)) or int(ops.argmax_rows(buf, V)[3]) == 77
+    assert int(ops.argmax_rows(buf, V)[3]) == 77
+
+
+def test_batched_decode_matches_single_sequence_runs(cuda_device):
+    """Batch-8 decode (per-sequence device state machines, ragged prompts) must reproduce each sequence decoded
+    alone (teacher-forced schedule so that bf16 argmax ties cannot make the runs diverge)."""
+    from oracle.weights import TINY, make_weights
+    from tests.helpers import build_product_model
+    model = build_product_model(TINY, make_weights(TINY), num_image_tokens=4)
+    model.eval()
+    g = torch.Generator().manual_seed(5)
+    B, P, steps = 4, 10, 14
+    lens = torch.tensor([10, 7, 9, 4], dtype=torch.int32)
+    prompts = torch.randint(0, 128000, (B, P), generator=g)
+    forced = torch.randint(0, 128000, (B, steps + 2), generator=g).to(torch.int32)
+    forced[0, 2] = 128256; forced[0, 9] = 128257          # image in sequence 0
+    forced[2, 0] = 128256                                    # image right away in sequence 2
+    forced[3, 6] = 128009                                    # EOS stops sequence 3 early
+    emb = model.get_model().embed_tokens(prompts.cuda())
+    for b in range(B):
+        emb[b, int(lens[b]):] = 0
+    ids, imgs = model.greedy_decode(None, None, emb, max_new_tokens=steps - 1, output_image=True,
+                                    prompt_lens=lens, forced_tokens=forced)
+    for b in range(B):
+        eb = emb[b:b + 1, :int(lens[b])].contiguous()
+        i1, im1 = model.greedy_decode(None, None, eb, max_new_tokens=steps - 1, output_image=True,
+                                      forced_tokens=forced[b:b + 1])
+        assert ids[b].cpu().tolist() == i1[0].cpu().tolist(), f"ids differ for sequence {b}"
+        assert imgs[b].shape[0] == (im1.shape[0] if im1.dim() == 2 else 0)
+        if imgs[b].shape[0]:
+            _close(imgs[b], im1, 3e-2, f"image embeds seq {b}")
+    assert ids[3].cpu().tolist()[-1] == 128009 and len(ids[3]) == 7
+    assert imgs[0].shape[0] == 4 and imgs[2].shape[0] == 4 and imgs[1].shape[0] == 0
