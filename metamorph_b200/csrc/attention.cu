@@ -255,7 +255,8 @@ flash_fwd_kernel(FwdParams p) {
 // delta[b,h,t] = sum_c dO[t,h,c] * O[t,h,c]; one warp per (token,head)
 __global__ void attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout,
                                   float* __restrict__ delta, long long ldo, long long lddo, int B,
-                                  int T, int Hq, int dh) {
+                                  int T, int Hq, int dh, float delta_scale, const float* __restrict__ lse,
+                                  float* __restrict__ lse2) {
   const int warps_per_block = blockDim.x >> 5, lane = threadIdx.x & 31;
   const long long total = (long long)B * T * Hq;
   for (long long w = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); w < total;
@@ -280,7 +281,9 @@ __global__ void attn_delta_kernel(const bf16* __restrict__ o, const bf16* __rest
     s = warp_sum(s);
     if (lane == 0) {
       const int b = (int)(tok / T), t = (int)(tok % T);
-      delta[((long long)b * Hq + h) * T + t] = s;
+      const long long off = ((long long)b * Hq + h) * T + t;
+      delta[off] = s * delta_scale;
+      if (lse2 != nullptr) lse2[off] = lse[off] * kLog2e;   // exp2-domain copy for the tcgen05 backward
     }
   }
 }
@@ -558,12 +561,13 @@ int launch_fwd(const FwdParams& p, cudaStream_t stream) {
 
 // Shared by the mma.sync and tcgen05 backward paths (declared in common.cuh).
 int mm_attn_bwd_delta_launch(const void* o, const void* dout, float* delta, long long ldo, long long lddo,
-                             int B, int T, int Hq, int head_dim, cudaStream_t stream) {
+                             int B, int T, int Hq, int head_dim, float delta_scale, const float* lse,
+                             float* lse2, cudaStream_t stream) {
   const long long total = (long long)B * T * Hq;
   long long blocks = ceil_div64(total, 8);
   if (blocks > (long long)mm_num_sms() * 16) blocks = (long long)mm_num_sms() * 16;
   attn_delta_kernel<<<(int)blocks, 256, 0, stream>>>((const bf16*)o, (const bf16*)dout, delta, ldo, lddo, B, T,
-                                                     Hq, head_dim);
+                                                     Hq, head_dim, delta_scale, lse, lse2);
   MM_CHECK_LAUNCH();
   return MM_OK;
 }
@@ -598,9 +602,10 @@ MM_API int mm_attn_fwd(const void* q, const void* k, const void* v, void* o, flo
 }
 
 // Workspace: delta [B*Hq*T] fp32 followed by dq_accum [B*T*Hq*128] fp32.
+// Workspace: delta [B*Hq*T] fp32, dq_accum [B*T*Hq*128] fp32, then (tcgen05 path) lse*log2e [B*Hq*T] fp32 + pad.
 MM_API long long mm_attn_bwd_workspace_bytes(int B, int T, int Hq) {
   const long long delta = ((long long)B * Hq * T * 4 + 255) / 256 * 256;
-  return delta + (long long)B * T * Hq * 128 * 4;
+  return delta + (long long)B * T * Hq * 128 * 4 + delta + 1024;
 }
 
 MM_API int mm_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout,
@@ -624,7 +629,7 @@ MM_API int mm_attn_bwd(const void* q, const void* k, const void* v, const void* 
     long long blocks = ceil_div64(total, 8);
     if (blocks > (long long)mm_num_sms() * 16) blocks = (long long)mm_num_sms() * 16;
     attn_delta_kernel<<<(int)blocks, 256, 0, stream>>>((const bf16*)o, (const bf16*)dout, delta, ldo,
-                                                       lddo, B, T, Hq, head_dim);
+                                                       lddo, B, T, Hq, head_dim, 1.f, nullptr, nullptr);
     MM_CHECK_LAUNCH();
   }
   BwdParams p;

@@ -63,6 +63,20 @@ __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_
       "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -613,11 +627,11 @@ namespace {
 
 constexpr int BT_THREADS = 576;  // TMA warp + MMA warp + 16 elementwise warps
 constexpr int BT_TILE = 32768;
-constexpr int BT_SMEM = 7 * BT_TILE + 1024 /*lse,delta*/ + 256 /*barriers*/ + 1024 /*align*/;
+constexpr int BT_SMEM = 7 * BT_TILE + 2048 /*lse,delta x2*/ + 256 /*barriers*/ + 768 /*align slack*/;
 
 struct TcBwdParams {
-  const float* lse;
-  const float* delta;
+  const float* lse;    // lse * log2(e)   [B,Hq,T]
+  const float* delta;  // rowsum(dO o O) * softmax_scale
   float* dq_accum;  // [B*T, Hq*128] fp32 (zeroed)
   bf16* dk;
   bf16* dv;
@@ -628,6 +642,13 @@ struct TcBwdParams {
   int dbg;  // timing experiments only (MM_ATTN_DBG): 1 skip dQ reds, 2 skip dS smem stores, 4 skip exp2, 8 skip MMA drain
 };
 
+// 1-D bulk copy global -> shared, completion counted on an mbarrier
+__device__ __forceinline__ void bulk_load(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_dst),
+               "l"(gsrc), "r"(bytes), "r"(bar)
+               : "memory");
+}
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
                : "memory");
@@ -640,17 +661,21 @@ flash_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  if (threadIdx.x == 0 && base - smem_u32(smem_raw) > 768u) {
+    printf("flash_bwd_tc_kernel: dynamic smem base misaligned beyond the reserved slack\n");
+    __trap();
+  }
   const uint32_t sK = base, sV = base + BT_TILE;
   const uint32_t sQ[2] = {base + 2 * BT_TILE, base + 4 * BT_TILE};
   const uint32_t sdO[2] = {base + 3 * BT_TILE, base + 5 * BT_TILE};
   const uint32_t sdS = base + 6 * BT_TILE;
-  float* sLse = reinterpret_cast<float*>(base_ptr + 7 * BT_TILE);
-  float* sDelta = sLse + 128;
-  const uint32_t bar = base + 7 * BT_TILE + 1024;
+  float* sStat = reinterpret_cast<float*>(base_ptr + 7 * BT_TILE);   // [2 buffers][lse 128 | delta 128]
+  const uint32_t uStat = base + 7 * BT_TILE;
+  const uint32_t bar = base + 7 * BT_TILE + 2048;
   const uint32_t kv_full = bar, qdo_full0 = bar + 8, qdo_full1 = bar + 16, qdo_empty0 = bar + 24,
                  qdo_empty1 = bar + 32, st_full = bar + 40, p_full = bar + 48, dq_full = bar + 56,
                  dq_empty = bar + 64, fin_full = bar + 72, mma_sync = bar + 80, tmem_slot = bar + 88;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + 7 * BT_TILE + 1024 + 88);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + 7 * BT_TILE + 2048 + 88);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int jt = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
@@ -700,7 +725,12 @@ flash_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       const int q0 = (qt_begin + it % n_qt) * 128;
       const uint32_t full = buf ? qdo_full1 : qdo_full0, empty = buf ? qdo_empty1 : qdo_empty0;
       mbar_wait(empty, (uint32_t)((use & 1) ^ 1));
-      mbar_arrive_expect_tx(full, 2 * BT_TILE);
+      mbar_arrive_expect_tx(full, 2 * BT_TILE + 1024);
+      {
+        const long long off = ((long long)b * p.Hq + hq) * p.T + q0;
+        bulk_load(uStat + buf * 1024, p.lse + off, 512, full);
+        bulk_load(uStat + buf * 1024 + 512, p.delta + off, 512, full);
+      }
       tma_load_2d(sQ[buf], &tmap_q, full, hq * 128, tok0 + q0);
       tma_load_2d(sQ[buf] + 16384, &tmap_q, full, hq * 128 + 64, tok0 + q0);
       tma_load_2d(sdO[buf], &tmap_do, full, hq * 128, tok0 + q0);
@@ -763,76 +793,81 @@ flash_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       const uint32_t ph = (uint32_t)(it & 1);
       const int hq = hk * G + it / n_qt;
       const int q0 = (qt_begin + it % n_qt) * 128;
-      asm volatile("bar.sync 1, 512;" ::: "memory");  // previous iteration's readers of sLse/sDelta are done
-      if (c == 0) {
-        const int qi = q0 + r;
-        const long long off = ((long long)b * p.Hq + hq) * p.T + (qi < p.T ? qi : 0);
-        sLse[r] = (qi < p.T) ? p.lse[off] * kLog2e : INFINITY;
-        sDelta[r] = (qi < p.T) ? p.delta[off] * p.scale : 0.f;
-      }
-      asm volatile("bar.sync 1, 512;" ::: "memory");
+      // lse*log2e and delta*scale of this query tile arrive with the Q/dO TMA transaction
+      const int sbuf = it & 1;
+      const float* sLse = sStat + sbuf * 256;
+      const float* sDelta = sLse + 128;
+      mbar_wait(sbuf ? qdo_full1 : qdo_full0, (uint32_t)((it >> 1) & 1));
       mbar_wait(st_full, ph);
       tcgen05_fence_after();
-      uint32_t s[32], dp[32];
-      tmem_ld_32x32b_x32(tST + lane_off + c * 32, s);
-      tmem_ld_32x32b_x32(tDPT + lane_off + c * 32, dp);
+      // two halves of 16 query columns keep the live register set small (no spills at 576 threads/CTA)
+      uint32_t s0[16], s1[16], dp0[16], dp1[16];
+      tmem_ld_32x32b_x16(tST + lane_off + c * 32, s0);
+      tmem_ld_32x32b_x16(tST + lane_off + c * 32 + 16, s1);
+      tmem_ld_32x32b_x16(tDPT + lane_off + c * 32, dp0);
+      tmem_ld_32x32b_x16(tDPT + lane_off + c * 32 + 16, dp1);
       tmem_ld_wait();
       // P^T / dS^T are packed over columns that other warps of this quadrant are still loading:
       // every load of the tile must have completed before the first store.
       asm volatile("bar.sync 2, 512;" ::: "memory");
       const bool diag = q0 < kv0 + 128;            // tile touches the causal boundary
       const bool tail = q0 + 128 > p.T;            // tile overhangs the sequence end
-      uint32_t pp[16], dd[16];
-      const float* lse_c = sLse + c * 32;
-      const float* del_c = sDelta + c * 32;
-      if (!diag && !tail) {
-        if (key_ok) {
+      const bool fast = !diag && !tail;
 #pragma unroll
-          for (int t = 0; t < 32; t += 4) {
-            const float4 l4 = *reinterpret_cast<const float4*>(lse_c + t);
-            const float4 d4 = *reinterpret_cast<const float4*>(del_c + t);
-            const float e0 = fast_exp2(fmaf(__uint_as_float(s[t]), sl2, -l4.x));
-            const float e1 = fast_exp2(fmaf(__uint_as_float(s[t + 1]), sl2, -l4.y));
-            const float e2 = fast_exp2(fmaf(__uint_as_float(s[t + 2]), sl2, -l4.z));
-            const float e3 = fast_exp2(fmaf(__uint_as_float(s[t + 3]), sl2, -l4.w));
-            pp[t >> 1] = pack_bf16x2(e0, e1);
-            pp[(t >> 1) + 1] = pack_bf16x2(e2, e3);
-            dd[t >> 1] = pack_bf16x2(e0 * fmaf(__uint_as_float(dp[t]), p.scale, -d4.x),
-                                     e1 * fmaf(__uint_as_float(dp[t + 1]), p.scale, -d4.y));
-            dd[(t >> 1) + 1] = pack_bf16x2(e2 * fmaf(__uint_as_float(dp[t + 2]), p.scale, -d4.z),
-                                           e3 * fmaf(__uint_as_float(dp[t + 3]), p.scale, -d4.w));
+      for (int hf = 0; hf < 2; ++hf) {
+        const uint32_t(&sv)[16] = hf ? s1 : s0;
+        const uint32_t(&dv_)[16] = hf ? dp1 : dp0;
+        const int cb = c * 32 + hf * 16;           // first query column of this half
+        uint32_t pp[8], dd[8];
+        if (fast) {
+          if (key_ok) {
+#pragma unroll
+            for (int t = 0; t < 16; t += 4) {
+              const float4 l4 = *reinterpret_cast<const float4*>(sLse + cb + t);
+              const float4 d4 = *reinterpret_cast<const float4*>(sDelta + cb + t);
+              const float e0 = fast_exp2(fmaf(__uint_as_float(sv[t]), sl2, -l4.x));
+              const float e1 = fast_exp2(fmaf(__uint_as_float(sv[t + 1]), sl2, -l4.y));
+              const float e2 = fast_exp2(fmaf(__uint_as_float(sv[t + 2]), sl2, -l4.z));
+              const float e3 = fast_exp2(fmaf(__uint_as_float(sv[t + 3]), sl2, -l4.w));
+              pp[t >> 1] = pack_bf16x2(e0, e1);
+              pp[(t >> 1) + 1] = pack_bf16x2(e2, e3);
+              dd[t >> 1] = pack_bf16x2(e0 * fmaf(__uint_as_float(dv_[t]), p.scale, -d4.x),
+                                       e1 * fmaf(__uint_as_float(dv_[t + 1]), p.scale, -d4.y));
+              dd[(t >> 1) + 1] = pack_bf16x2(e2 * fmaf(__uint_as_float(dv_[t + 2]), p.scale, -d4.z),
+                                             e3 * fmaf(__uint_as_float(dv_[t + 3]), p.scale, -d4.w));
+            }
+          } else {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) pp[t] = dd[t] = 0u;
           }
         } else {
 #pragma unroll
-          for (int t = 0; t < 16; ++t) pp[t] = dd[t] = 0u;
-        }
-      } else {
+          for (int t = 0; t < 16; t += 2) {
+            float pv[2], dvv[2];
 #pragma unroll
-        for (int t = 0; t < 32; t += 2) {
-          float pv[2], dv[2];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int qq = c * 32 + t + u;
-            const int q_idx = q0 + qq;
-            const bool ok = key_ok && (q_idx < p.T) && (key_idx <= q_idx);
-            const float e = ok ? fast_exp2(fmaf(__uint_as_float(s[t + u]), sl2, -sLse[qq])) : 0.f;
-            pv[u] = e;
-            dv[u] = e * fmaf(__uint_as_float(dp[t + u]), p.scale, -sDelta[qq]);
+            for (int u = 0; u < 2; ++u) {
+              const int qq = cb + t + u;
+              const int q_idx = q0 + qq;
+              const bool ok = key_ok && (q_idx < p.T) && (key_idx <= q_idx);
+              const float e = ok ? fast_exp2(fmaf(__uint_as_float(sv[t + u]), sl2, -sLse[qq])) : 0.f;
+              pv[u] = e;
+              dvv[u] = e * fmaf(__uint_as_float(dv_[t + u]), p.scale, -sDelta[qq]);
+            }
+            pp[t >> 1] = pack_bf16x2(pv[0], pv[1]);
+            dd[t >> 1] = pack_bf16x2(dvv[0], dvv[1]);
           }
-          pp[t >> 1] = pack_bf16x2(pv[0], pv[1]);
-          dd[t >> 1] = pack_bf16x2(dv[0], dv[1]);
         }
-      }
-      tmem_st_32x32b_x16(tST + lane_off + c * 16, pp);
-      tmem_st_32x32b_x16(tDPT + lane_off + c * 16, dd);
-      // dS^T row -> smem in the SW128 MN-major layout (two [128 keys x 64 q] boxes, 16-byte chunks
-      // XOR-swizzled with key%8) so that the dQ MMA can read it as its A operand.
+        tmem_st_32x32b_x8(tST + lane_off + c * 16 + hf * 8, pp);
+        tmem_st_32x32b_x8(tDPT + lane_off + c * 16 + hf * 8, dd);
+        // dS^T row -> smem in the SW128 MN-major layout (two [128 keys x 64 q] boxes, 16-byte chunks
+        // XOR-swizzled with key%8) so that the dQ MMA can read it as its A operand.
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int c8 = c * 4 + i;
-        const int slot = (c8 & 7) ^ (r & 7);
-        *reinterpret_cast<int4*>(dS_row + (c8 >> 3) * 16384 + slot * 16) =
-            make_int4(dd[4 * i], dd[4 * i + 1], dd[4 * i + 2], dd[4 * i + 3]);
+        for (int i = 0; i < 2; ++i) {
+          const int c8 = c * 4 + hf * 2 + i;
+          const int slot = (c8 & 7) ^ (r & 7);
+          *reinterpret_cast<int4*>(dS_row + (c8 >> 3) * 16384 + slot * 16) =
+              make_int4(dd[4 * i], dd[4 * i + 1], dd[4 * i + 2], dd[4 * i + 3]);
+        }
       }
       tmem_st_wait();
       fence_proxy_async_smem();
@@ -910,15 +945,19 @@ MM_API int mm_attn_bwd_tc(const void* q, const void* k, const void* v, const voi
   MM_CHECK_ARG(head_dim == 128, "mm_attn_bwd_tc: head_dim must be 128");
   MM_CHECK_ARG(B > 0 && T > 0 && Hq % Hkv == 0, "mm_attn_bwd_tc: bad shape");
   const long long delta_bytes = ((long long)B * Hq * T * 4 + 255) / 256 * 256;
-  MM_CHECK_ARG(workspace != nullptr && workspace_bytes >= delta_bytes + (long long)B * T * Hq * 128 * 4,
-               "mm_attn_bwd_tc: workspace too small");
+  MM_CHECK_ARG(workspace != nullptr &&
+                   workspace_bytes >= 2 * delta_bytes + (long long)B * T * Hq * 128 * 4 + 1024,
+               "mm_attn_bwd_tc: workspace too small (use mm_attn_bwd_workspace_bytes)");
+  MM_CHECK_ARG(T % 4 == 0, "mm_attn_bwd_tc: T must be a multiple of 4 (16-byte aligned statistics rows)");
   MM_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && lddo % 8 == 0 && lddq % 8 == 0 &&
                    lddk % 8 == 0 && lddv % 8 == 0, "mm_attn_bwd_tc: pitches %% 8");
   float* delta = reinterpret_cast<float*>(workspace);
   float* dq_accum = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + delta_bytes);
   MM_CHECK_CUDA(cudaMemsetAsync(dq_accum, 0, (size_t)B * T * Hq * 128 * 4, stream));
+  float* lse2 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(dq_accum) + (size_t)B * T * Hq * 128 * 4);
   int rc;
-  if ((rc = mm_attn_bwd_delta_launch(o, dout, delta, ldo, lddo, B, T, Hq, head_dim, stream))) return rc;
+  if ((rc = mm_attn_bwd_delta_launch(o, dout, delta, ldo, lddo, B, T, Hq, head_dim, scale, lse, lse2, stream)))
+    return rc;
   CUtensorMap tq, tk, tv, tdo;
   if ((rc = make_tmap_rows(&tq, q, (long long)Hq * 128, (long long)B * T, ldq))) return rc;
   if ((rc = make_tmap_rows(&tk, k, (long long)Hkv * 128, (long long)B * T, ldk))) return rc;
@@ -931,7 +970,7 @@ MM_API int mm_attn_bwd_tc(const void* q, const void* k, const void* v, const voi
   });
   MM_CHECK_CUDA(err);
   TcBwdParams p;
-  p.lse = lse; p.delta = delta; p.dq_accum = dq_accum; p.dk = (bf16*)dk; p.dv = (bf16*)dv; p.seqlens = seqlens;
+  p.lse = lse2; p.delta = delta; p.dq_accum = dq_accum; p.dk = (bf16*)dk; p.dv = (bf16*)dv; p.seqlens = seqlens;
   p.lddk = lddk; p.lddv = lddv; p.B = B; p.T = T; p.Hq = Hq; p.Hkv = Hkv; p.scale = scale;
   {
     const char* e = getenv("MM_ATTN_DBG");

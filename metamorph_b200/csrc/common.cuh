@@ -48,7 +48,8 @@ static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b;
 
 int mm_num_sms();
 int mm_attn_bwd_delta_launch(const void* o, const void* dout, float* delta, long long ldo, long long lddo,
-                             int B, int T, int Hq, int head_dim, cudaStream_t stream);
+                             int B, int T, int Hq, int head_dim, float delta_scale, const float* lse,
+                             float* lse2, cudaStream_t stream);
 int mm_attn_bwd_convert_launch(const float* dq_accum, void* dq, long long R, int C, long long lddq,
                                cudaStream_t stream);
 

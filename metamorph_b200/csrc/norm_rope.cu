@@ -63,17 +63,18 @@ rmsnorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16*
 // dx = dres_in + rstd*dy*w - x * rstd^3 * sum(dy*w*x)/H ;  dw += sum_rows dy * x * rstd  (fp32 atomics)
 // Both row statistics (sum x^2 and sum dy*w*x) come from ONE pass and ONE block reduction per row
 // (double-buffered smem scratch -> a single __syncthreads per row).
-__global__ void __launch_bounds__(kNormThreads)
+template <int VPT>   // 8-element vectors per thread (H <= 8 * 256 * VPT): sized to H so registers stay low
+__global__ void __launch_bounds__(kNormThreads, (VPT <= 2 ? 3 : 1))
 rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                    const bf16* __restrict__ w, const bf16* __restrict__ dres_in,
                    bf16* __restrict__ dx, float* __restrict__ dw_accum, int M, int H, float eps) {
   __shared__ float red[2][2][kNormThreads / 32];
   const int nvec = H >> 3;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float dwp[kMaxVec][8];
-  float wv[kMaxVec][8];
+  float dwp[VPT][8];
+  float wv[VPT][8];
 #pragma unroll
-  for (int i = 0; i < kMaxVec; ++i) {
+  for (int i = 0; i < VPT; ++i) {
     const int v = threadIdx.x + i * kNormThreads;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -85,10 +86,10 @@ rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
   for (int row = blockIdx.x; row < M; row += gridDim.x, par ^= 1) {
     const bf16* xr = x + (size_t)row * H;
     const bf16* dyr = dy + (size_t)row * H;
-    float xv[kMaxVec][8], gv[kMaxVec][8];
+    float xv[VPT][8], gv[VPT][8];
     float ss = 0.f, gwx = 0.f;
 #pragma unroll
-    for (int i = 0; i < kMaxVec; ++i) {
+    for (int i = 0; i < VPT; ++i) {
       const int v = threadIdx.x + i * kNormThreads;
       if (v < nvec) {
         const int4 rx = ld_nc_int4(xr + v * 8);
@@ -117,7 +118,7 @@ rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
     const float coef = rstd * rstd * rstd * tg / (float)H;
     bf16* dxr = dx + (size_t)row * H;
 #pragma unroll
-    for (int i = 0; i < kMaxVec; ++i) {
+    for (int i = 0; i < VPT; ++i) {
       const int v = threadIdx.x + i * kNormThreads;
       if (v < nvec) {
         float o[8];
@@ -144,7 +145,7 @@ rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
   }
   if (dw_accum != nullptr) {
 #pragma unroll
-    for (int i = 0; i < kMaxVec; ++i) {
+    for (int i = 0; i < VPT; ++i) {
       const int v = threadIdx.x + i * kNormThreads;
       if (v < nvec) {
 #pragma unroll
@@ -268,11 +269,17 @@ MM_API int mm_rmsnorm_bwd(const void* dy, const void* x, const void* w, const vo
                           float* dw_accum, long long M, long long H, float eps, cudaStream_t stream) {
   MM_CHECK_ARG(M > 0 && H > 0 && H % 8 == 0 && H <= 8 * kNormThreads * kMaxVec,
                "mm_rmsnorm_bwd: need H%%8==0 and H<=%d (H=%lld)", 8 * kNormThreads * kMaxVec, H);
-  const int cap = mm_num_sms() * 8;
+  const int cap = mm_num_sms() * 6;
   const int grid = M < cap ? (int)M : cap;
-  rmsnorm_bwd_kernel<<<grid, kNormThreads, 0, stream>>>((const bf16*)dy, (const bf16*)x,
-                                                        (const bf16*)w, (const bf16*)dres_in,
-                                                        (bf16*)dx, dw_accum, (int)M, (int)H, eps);
+  const int vpt = (int)((H / 8 + kNormThreads - 1) / kNormThreads);
+#define MM_RMS_BWD(V)                                                                                      \
+  rmsnorm_bwd_kernel<V><<<grid, kNormThreads, 0, stream>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, \
+                                                           (const bf16*)dres_in, (bf16*)dx, dw_accum, (int)M, \
+                                                           (int)H, eps)
+  if (vpt <= 1) MM_RMS_BWD(1);
+  else if (vpt == 2) MM_RMS_BWD(2);
+  else MM_RMS_BWD(4);
+#undef MM_RMS_BWD
   MM_CHECK_LAUNCH();
   return MM_OK;
 }
