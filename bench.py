@@ -354,6 +354,8 @@ def main():
                            "l2_policy": "inputs+weights (>100 GB/step) far exceed the 126 MB L2; no flush needed",
                            "max_grad_norm": None, "optimizer": "AdamW (fused into backward, fp32 master/m/v)",
                            "recompute": f"gate/up GEMM recomputed in {args.layers - min(args.save_gu_layers, args.layers)} of {args.layers} layers; norms always",
+                           "lm_head_rows": "lm_head+CE run on the %d of %d rows that carry a label (identical loss/grads; "
+                                           "algorithmic FLOPs below still count all rows)" % engine.hot.last_head_rows,
                            "loss": loss_val,
                            "peak_hbm_gb": round(torch.cuda.max_memory_allocated() / 1e9, 1)},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "decode": decode, "gpu_launches": launches, "clocks": clocks}

@@ -31,7 +31,8 @@ int mm_check_device(void); /* 0 iff the current device is sm_100 */
  *   a_mn_major=0: A is [M,K];  =1: A stored [K,M] (A^T is used).   b_mn_major=0: B is [N,K] (C = A B^T);
  *   =1: B stored [K,N] (C = A B).  epilogue: 0 store, 1 +bias, 2 +bias,GELU(erf), 3 +bias,GELU(tanh),
  *   4 +residual, 5 +bias+residual, 6 SwiGLU over [16 gate|16 up] interleaved columns (C is [M,N/2], aux gets
- *   the raw [M,N] gate|up). out_f32: C is fp32. accumulate: C += result. force_bn: 0 auto, 128, 256. */
+ *   the raw [M,N] gate|up), 7 SwiGLU backward fused into the down_proj dgrad (acc = d act; aux = gate|up [M,2N]
+ *   overwritten with its gradient; C = recomputed act). out_f32: C is fp32. accumulate: C += result. force_bn: 0 auto, 128, 256. */
 int mm_gemm_bf16(const void* A, const void* B, void* C, const void* bias, const void* resid, void* aux,
                  long long M, long long N, long long K, long long lda, long long ldb, long long ldc,
                  long long ldr, long long ld_aux, int a_mn_major, int b_mn_major, int epilogue, int out_f32,

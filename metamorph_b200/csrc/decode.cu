@@ -40,16 +40,17 @@ skinny_gemm_kernel(const bf16* __restrict__ x, long long ldx, const bf16* __rest
   const bf16* xrow = x + (long long)g * ldx;  // batch row g (B operand column)
   const bool xok = g < m;
   const int nchunks = K >> 5;
-  // warp w handles k32-chunks w, w+8, ...; unrolled by 2 for memory-level parallelism
-  for (int c = warp; c < nchunks; c += 2 * (SK_THREADS / 32)) {
-    const int c2 = c + SK_THREADS / 32;
-    const bool has2 = c2 < nchunks;
-    int4 wa[2][G][2];
-    int4 xb[2];
+  // warp w handles k32-chunks w, w+8, ...; unrolled by UNR so that each lane keeps 2*G*UNR independent
+  // 128-bit weight loads in flight (the kernel is a pure HBM stream: bytes in flight per SM set its rate)
+  constexpr int UNR = (G == 1) ? 4 : 2;
+  constexpr int NW = SK_THREADS / 32;
+  for (int c = warp; c < nchunks; c += UNR * NW) {
+    int4 wa[UNR][G][2];
+    int4 xb[UNR];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int cc = u == 0 ? c : c2;
-      const bool ok = u == 0 || has2;
+    for (int u = 0; u < UNR; ++u) {
+      const int cc = c + u * NW;
+      const bool ok = cc < nchunks;
       const int k0 = cc * 32 + t * 8;
 #pragma unroll
       for (int i = 0; i < G; ++i) {
@@ -60,7 +61,7 @@ skinny_gemm_kernel(const bf16* __restrict__ x, long long ldx, const bf16* __rest
       xb[u] = (ok && xok) ? *reinterpret_cast<const int4*>(xrow + k0) : make_int4(0, 0, 0, 0);
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < UNR; ++u) {
 #pragma unroll
       for (int i = 0; i < G; ++i) {
         // k-permutation: lane t owns k = 8t..8t+7 of the chunk; MMA #1 uses elements {0,1 | 2,3},

@@ -33,6 +33,8 @@ enum Epilogue : int {
   EPI_RESID = 4,           // C = acc + R[m,n]                   (o_proj / down_proj + residual)
   EPI_BIAS_RESID = 5,      // C = acc + bias[n] + R[m,n]         (SigLIP out_proj / fc2)
   EPI_SWIGLU = 6,          // columns interleaved [16 gate | 16 up]: C[m, n/2] = silu(g) * u
+  EPI_SWIGLU_BWD = 7,      // acc = d(act)[m, n]; aux holds (gate|up)[m, 2n] interleaved and is overwritten
+                           // with d(gate|up); C[m, n] = silu(g) * u (recomputed activation for the wgrad)
 };
 
 struct EpiParams {
@@ -217,6 +219,43 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * ep.alpha;
         const bool full_chunk = (col0 + 32 <= N);
 
+        if (ep.epi == EPI_SWIGLU_BWD) {
+          // LlamaMLP backward fused into the down_proj dgrad: this thread owns d(act) for 32 intermediate
+          // channels of one token = two [16 gate | 16 up] blocks of the interleaved gate/up buffer.
+          if (row_ok) {
+            bf16* gp = ep.aux + (long long)row * ep.ld_aux + 2 * col0;
+            bf16* cp = reinterpret_cast<bf16*>(ep.C) + (long long)row * ep.ldc + col0;
+#pragma unroll
+            for (int blk = 0; blk < 2; ++blk) {
+              uint32_t og[8], ou[8], oa[8];
+#pragma unroll
+              for (int hv = 0; hv < 2; ++hv) {
+                const int4 graw = *reinterpret_cast<const int4*>(gp + blk * 32 + hv * 8);
+                const int4 uraw = *reinterpret_cast<const int4*>(gp + blk * 32 + 16 + hv * 8);
+                const uint32_t ug[4] = {(uint32_t)graw.x, (uint32_t)graw.y, (uint32_t)graw.z, (uint32_t)graw.w};
+                const uint32_t uu[4] = {(uint32_t)uraw.x, (uint32_t)uraw.y, (uint32_t)uraw.z, (uint32_t)uraw.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 g = unpack_bf16x2(ug[j]);
+                  const float2 u = unpack_bf16x2(uu[j]);
+                  const float d0 = v[blk * 16 + hv * 8 + 2 * j], d1 = v[blk * 16 + hv * 8 + 2 * j + 1];
+                  const float s0 = 1.f / (1.f + __expf(-g.x)), s1 = 1.f / (1.f + __expf(-g.y));
+                  const float a0 = g.x * s0, a1 = g.y * s1;
+                  oa[hv * 4 + j] = pack_bf16x2(a0 * u.x, a1 * u.y);
+                  og[hv * 4 + j] = pack_bf16x2(d0 * u.x * (s0 + a0 * (1.f - s0)), d1 * u.y * (s1 + a1 * (1.f - s1)));
+                  ou[hv * 4 + j] = pack_bf16x2(d0 * a0, d1 * a1);
+                }
+              }
+              *reinterpret_cast<int4*>(gp + blk * 32) = make_int4(og[0], og[1], og[2], og[3]);
+              *reinterpret_cast<int4*>(gp + blk * 32 + 8) = make_int4(og[4], og[5], og[6], og[7]);
+              *reinterpret_cast<int4*>(gp + blk * 32 + 16) = make_int4(ou[0], ou[1], ou[2], ou[3]);
+              *reinterpret_cast<int4*>(gp + blk * 32 + 24) = make_int4(ou[4], ou[5], ou[6], ou[7]);
+              *reinterpret_cast<int4*>(cp + blk * 16) = make_int4(oa[0], oa[1], oa[2], oa[3]);
+              *reinterpret_cast<int4*>(cp + blk * 16 + 8) = make_int4(oa[4], oa[5], oa[6], oa[7]);
+            }
+          }
+          continue;
+        }
         if (ep.epi == EPI_SWIGLU) {
           // chunk = 16 gate columns followed by their 16 up columns
           if (row_ok) {
@@ -421,8 +460,12 @@ MM_API int mm_gemm_bf16(const void* A, const void* B, void* C, const void* bias,
                             cudaStream_t stream) {
   MM_CHECK_ARG(M > 0 && N > 0 && K > 0, "mm_gemm_bf16: empty problem M=%lld N=%lld K=%lld", M, N, K);
   MM_CHECK_ARG(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "mm_gemm_bf16: dims too large");
-  MM_CHECK_ARG(epilogue >= EPI_STORE && epilogue <= EPI_SWIGLU, "mm_gemm_bf16: bad epilogue %d",
+  MM_CHECK_ARG(epilogue >= EPI_STORE && epilogue <= EPI_SWIGLU_BWD, "mm_gemm_bf16: bad epilogue %d",
                epilogue);
+  if (epilogue == EPI_SWIGLU_BWD)
+    MM_CHECK_ARG(N % 32 == 0 && !out_f32 && !accumulate && aux != nullptr && ld_aux % 8 == 0 &&
+                     ((uintptr_t)aux & 15) == 0,
+                 "mm_gemm_bf16: SWIGLU_BWD epilogue needs N%%32==0, bf16 out and a 16B-aligned gate|up buffer");
   MM_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && ((uintptr_t)C & 15) == 0,
                "mm_gemm_bf16: A/B/C must be 16-byte aligned");
   MM_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0, "mm_gemm_bf16: lda/ldb must be multiples of 8 elements");

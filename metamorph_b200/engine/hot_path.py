@@ -74,6 +74,7 @@ class HotPath:
     def __init__(self, model):
         self.m = model  # MetaMorphLlamaForCausalLM
         self.ce_chunk_rows = 2048
+        self.skip_unlabelled_rows = True
 
     # ------------------------------------------------------------------ vision side (A1, A2)
     def encode_images_train(self, images):
@@ -129,14 +130,28 @@ class HotPath:
         if use_vision_ar and img_loss_is_lang:
             ce_grad_mult = 1.0 + vision_coef   # loss = loss + coef * loss
 
+        # Rows whose shifted label is IGNORE_INDEX contribute neither to the loss nor to any gradient, and
+        # in training mode the logits are not returned: run lm_head / CE / dgrad / wgrad only on the rows that
+        # carry a label (identical loss and gradients; the reference computes all [B,T,V] logits because it
+        # returns them, metamorph_llama.py:398-413).
+        compact = self.skip_unlabelled_rows and not want_logits and 0 < n_valid < M
+        self.last_head_rows = (n_valid if compact else M, M)
+        if compact:
+            vrows = torch.nonzero(shift.reshape(-1) != IGNORE_INDEX).reshape(-1).to(torch.int32).to(dev, non_blocking=True)
+            h_src = ops.gather_rows(hidden, vrows)
+            lab_src = shift.reshape(-1)[shift.reshape(-1) != IGNORE_INDEX].to(torch.int32).to(dev, non_blocking=True)
+        else:
+            h_src, lab_src = hidden, shift_dev
+        Ms = h_src.shape[0]
         d_hidden = None
+        d_src = None
         if want_grad:
-            d_hidden = torch.empty_like(hidden)
+            d_src = torch.empty_like(h_src)
             g_lm = grads.get("lm_head.weight", m.lm_head.weight, fp32=True)
         R = self.ce_chunk_rows
-        for r0 in range(0, M, R):
-            r1 = min(M, r0 + R)
-            hs = hidden[r0:r1]
+        for r0 in range(0, Ms, R):
+            r1 = min(Ms, r0 + R)
+            hs = h_src[r0:r1]
             if want_logits:
                 lg = buf[r0:r1]
             else:
@@ -145,13 +160,19 @@ class HotPath:
                 ops.gemm(hs, m.lm_head.weight.data, out=cbuf[:, :V], out_dtype=torch.float32)
             if want_grad:
                 dl = torch.empty((r1 - r0, ldv), dtype=torch.bfloat16, device=dev)
-                ops.ce_fwd_bwd(lg, shift_dev[r0:r1], V, loss_lang, dlogits=dl, grad_scale=ce_scale * ce_grad_mult)
-                ops.gemm(dl[:, :V], m.lm_head.weight.data, b_mn=True, out=d_hidden[r0:r1])
+                ops.ce_fwd_bwd(lg, lab_src[r0:r1], V, loss_lang, dlogits=dl, grad_scale=ce_scale * ce_grad_mult)
+                ops.gemm(dl[:, :V], m.lm_head.weight.data, b_mn=True, out=d_src[r0:r1])
                 ops.gemm(dl[:, :V], hs, a_mn=True, b_mn=True, out=g_lm, out_dtype=torch.float32,
                          accumulate=(r0 > 0))
                 del dl
             else:
-                ops.ce_fwd_bwd(lg, shift_dev[r0:r1], V, loss_lang)
+                ops.ce_fwd_bwd(lg, lab_src[r0:r1], V, loss_lang)
+        if want_grad:
+            if compact:
+                d_hidden = torch.zeros_like(hidden)
+                ops.scatter_add_rows_(d_hidden, vrows, d_src)
+            else:
+                d_hidden = d_src
         if n_valid > 0:
             loss_lang = loss_lang * ce_scale
         else:  # CrossEntropyLoss(mean) over zero valid targets is NaN in the reference

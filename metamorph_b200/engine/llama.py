@@ -166,7 +166,6 @@ class LlamaStack:
         Hq, Hkv, dh = d.n_heads, d.n_kv_heads, d.head_dim
         M = dx_out.shape[0]
         # ---- MLP: out = h_mid + down(swiglu(gate_up(norm2(h_mid))))
-        dact = ops.gemm(dx_out, w.wd, b_mn=True)                                  # [M, I]
         n2 = ops.rmsnorm(s.h_mid, w.ln2, d.rms_eps)
         if s.gu is not None:
             gu = s.gu
@@ -174,9 +173,10 @@ class LlamaStack:
             gu = torch.empty((M, 2 * d.intermediate), dtype=torch.bfloat16, device=dx_out.device)
             tmp = ops.gemm(n2, w.wgu, aux=gu, epilogue=ops.EPI_SWIGLU)
             del tmp
+        # d(act) = dout * Wd with the SwiGLU backward fused into the epilogue: d(act) is never written,
+        # gu <- d(gate|up) in place, act = silu(g)*u recomputed for the down_proj wgrad
         act = torch.empty((M, d.intermediate), dtype=torch.bfloat16, device=dx_out.device)
-        ops.swiglu_bwd(gu, dact, dgu=gu, act=act)                                  # gu <- d(gate|up)
-        del dact
+        ops.gemm(dx_out, w.wd, b_mn=True, out=act, aux=gu, epilogue=ops.EPI_SWIGLU_BWD)
         ops.gemm(dx_out, act, a_mn=True, b_mn=True, out=g.wd, accumulate=accumulate)   # dWd = dout^T act
         del act
         ops.gemm(gu, n2, a_mn=True, b_mn=True, out=g.wgu, accumulate=accumulate)       # dWgu = dgu^T n2

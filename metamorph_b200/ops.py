@@ -8,7 +8,7 @@ import torch
 
 from ._lib import call, c_float, c_int, ll, ptr, require_cuda, stream_ptr
 
-EPI_STORE, EPI_BIAS, EPI_BIAS_GELU_ERF, EPI_BIAS_GELU_TANH, EPI_RESID, EPI_BIAS_RESID, EPI_SWIGLU = range(7)
+EPI_STORE, EPI_BIAS, EPI_BIAS_GELU_ERF, EPI_BIAS_GELU_TANH, EPI_RESID, EPI_BIAS_RESID, EPI_SWIGLU, EPI_SWIGLU_BWD = range(8)
 
 
 ATTN_BWD_TC = True  # tcgen05 backward (csrc/attention_tc.cu); the mma.sync kernel stays selectable with tc=False

@@ -69,6 +69,23 @@ def test_gemm_epilogues(cuda_device):
     g, u = a.float() @ wg.float().t(), a.float() @ wu.float().t()
     _close(act, F.silu(g) * u, 1e-2, "swiglu")
     _close(aux, (a.float() @ wgu.float().t()), 1e-2, "swiglu aux")
+    # SwiGLU backward fused into the down_proj dgrad epilogue: acc = d(act), aux = gate|up -> d(gate|up), C = act
+    from metamorph_b200.engine.packing import deinterleave_gate_up
+    I = 512
+    dy = torch.randn(M, 320, device=cuda_device).bfloat16()
+    wd = (torch.randn(320, I, device=cuda_device) * 0.05).bfloat16()            # down_proj weight [H, I]
+    g_ = torch.randn(M, I, device=cuda_device).bfloat16()
+    u_ = torch.randn(M, I, device=cuda_device).bfloat16()
+    gu = interleave_gate_up(g_.t().contiguous(), u_.t().contiguous()).t().contiguous()   # [M, 2I]
+    gf, uf = g_.float().requires_grad_(True), u_.float().requires_grad_(True)
+    dact_ref = dy.float() @ wd.float()
+    (F.silu(gf) * uf).backward(dact_ref)
+    act2 = torch.empty(M, I, device=cuda_device, dtype=torch.bfloat16)
+    ops.gemm(dy, wd, b_mn=True, out=act2, aux=gu, epilogue=ops.EPI_SWIGLU_BWD)
+    dg, du = deinterleave_gate_up(gu.t().contiguous())
+    _close(act2, F.silu(g_.float()) * u_.float(), 1e-2, "fused swiglu_bwd act")
+    _close(dg.t(), gf.grad, 2e-2, "fused swiglu_bwd dgate")
+    _close(du.t(), uf.grad, 2e-2, "fused swiglu_bwd dup")
 
 
 def test_rmsnorm_fwd_bwd(cuda_device):
