@@ -17,6 +17,7 @@
 // The accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of i+1.
 #include "common.cuh"
 #include <mutex>
+#include <stdlib.h>
 
 namespace {
 
@@ -69,6 +70,157 @@ __device__ __forceinline__ uint64_t make_desc_base(bool mn_major) {
   return (lbo << 16) | (sbo << 32) | (1ull << 46) | (2ull << 61);
 }
 
+// Fused epilogue for one 32-column accumulator chunk held by one thread (one output row).
+__device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, float (&v)[32], int row, bool row_ok,
+                                               int col0, int N) {
+    const bool full_chunk = (col0 + 32 <= N);
+
+    if (ep.epi == EPI_SWIGLU_BWD) {
+      // LlamaMLP backward fused into the down_proj dgrad: this thread owns d(act) for 32 intermediate
+      // channels of one token = two [16 gate | 16 up] blocks of the interleaved gate/up buffer.
+      if (row_ok) {
+        bf16* gp = ep.aux + (long long)row * ep.ld_aux + 2 * col0;
+        bf16* cp = reinterpret_cast<bf16*>(ep.C) + (long long)row * ep.ldc + col0;
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk) {
+          uint32_t og[8], ou[8], oa[8];
+#pragma unroll
+          for (int hv = 0; hv < 2; ++hv) {
+            const int4 graw = *reinterpret_cast<const int4*>(gp + blk * 32 + hv * 8);
+            const int4 uraw = *reinterpret_cast<const int4*>(gp + blk * 32 + 16 + hv * 8);
+            const uint32_t ug[4] = {(uint32_t)graw.x, (uint32_t)graw.y, (uint32_t)graw.z, (uint32_t)graw.w};
+            const uint32_t uu[4] = {(uint32_t)uraw.x, (uint32_t)uraw.y, (uint32_t)uraw.z, (uint32_t)uraw.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 g = unpack_bf16x2(ug[j]);
+              const float2 u = unpack_bf16x2(uu[j]);
+              const float d0 = v[blk * 16 + hv * 8 + 2 * j], d1 = v[blk * 16 + hv * 8 + 2 * j + 1];
+              const float s0 = 1.f / (1.f + __expf(-g.x)), s1 = 1.f / (1.f + __expf(-g.y));
+              const float a0 = g.x * s0, a1 = g.y * s1;
+              oa[hv * 4 + j] = pack_bf16x2(a0 * u.x, a1 * u.y);
+              og[hv * 4 + j] = pack_bf16x2(d0 * u.x * (s0 + a0 * (1.f - s0)), d1 * u.y * (s1 + a1 * (1.f - s1)));
+              ou[hv * 4 + j] = pack_bf16x2(d0 * a0, d1 * a1);
+            }
+          }
+          *reinterpret_cast<int4*>(gp + blk * 32) = make_int4(og[0], og[1], og[2], og[3]);
+          *reinterpret_cast<int4*>(gp + blk * 32 + 8) = make_int4(og[4], og[5], og[6], og[7]);
+          *reinterpret_cast<int4*>(gp + blk * 32 + 16) = make_int4(ou[0], ou[1], ou[2], ou[3]);
+          *reinterpret_cast<int4*>(gp + blk * 32 + 24) = make_int4(ou[4], ou[5], ou[6], ou[7]);
+          *reinterpret_cast<int4*>(cp + blk * 16) = make_int4(oa[0], oa[1], oa[2], oa[3]);
+          *reinterpret_cast<int4*>(cp + blk * 16 + 8) = make_int4(oa[4], oa[5], oa[6], oa[7]);
+        }
+      }
+      return;
+    }
+    if (ep.epi == EPI_SWIGLU) {
+      // chunk = 16 gate columns followed by their 16 up columns
+      if (row_ok) {
+        if (ep.aux != nullptr) {
+          bf16* ap = ep.aux + (long long)row * ep.ld_aux + col0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            int4 o;
+            o.x = pack_bf16x2(v[j], v[j + 1]);
+            o.y = pack_bf16x2(v[j + 2], v[j + 3]);
+            o.z = pack_bf16x2(v[j + 4], v[j + 5]);
+            o.w = pack_bf16x2(v[j + 6], v[j + 7]);
+            *reinterpret_cast<int4*>(ap + j) = o;
+          }
+        }
+        float o16[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o16[j] = silu(v[j]) * v[16 + j];
+        bf16* cp = reinterpret_cast<bf16*>(ep.C) + (long long)row * ep.ldc + (col0 >> 1);
+#pragma unroll
+        for (int j = 0; j < 16; j += 8) {
+          int4 o;
+          o.x = pack_bf16x2(o16[j], o16[j + 1]);
+          o.y = pack_bf16x2(o16[j + 2], o16[j + 3]);
+          o.z = pack_bf16x2(o16[j + 4], o16[j + 5]);
+          o.w = pack_bf16x2(o16[j + 6], o16[j + 7]);
+          *reinterpret_cast<int4*>(cp + j) = o;
+        }
+      }
+      return;
+    }
+
+    if (ep.epi == EPI_BIAS || ep.epi == EPI_BIAS_GELU_ERF || ep.epi == EPI_BIAS_GELU_TANH ||
+        ep.epi == EPI_BIAS_RESID) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (full_chunk || col0 + j < N) v[j] += __bfloat162float(__ldg(ep.bias + col0 + j));
+    }
+    if (ep.epi == EPI_BIAS_GELU_ERF) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+    } else if (ep.epi == EPI_BIAS_GELU_TANH) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
+    }
+    if (!row_ok) return;  // lanes past M only take part in the TMEM load
+    if (ep.epi == EPI_RESID || ep.epi == EPI_BIAS_RESID) {
+      const bf16* rp = ep.resid + (long long)row * ep.ldr + col0;
+      if (full_chunk) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          const int4 rr = *reinterpret_cast<const int4*>(rp + j);
+          float2 f;
+          f = unpack_bf16x2(rr.x); v[j] += f.x; v[j + 1] += f.y;
+          f = unpack_bf16x2(rr.y); v[j + 2] += f.x; v[j + 3] += f.y;
+          f = unpack_bf16x2(rr.z); v[j + 4] += f.x; v[j + 5] += f.y;
+          f = unpack_bf16x2(rr.w); v[j + 6] += f.x; v[j + 7] += f.y;
+        }
+      } else {
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < N) v[j] += __bfloat162float(rp[j]);
+      }
+    }
+    if (ep.out_f32) {
+      float* cp = reinterpret_cast<float*>(ep.C) + (long long)row * ep.ldc + col0;
+      if (full_chunk) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          if (ep.accumulate) {
+            const float4 old = *reinterpret_cast<const float4*>(cp + j);
+            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+          }
+          *reinterpret_cast<float4*>(cp + j) = o;
+        }
+      } else {
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < N) cp[j] = ep.accumulate ? cp[j] + v[j] : v[j];
+      }
+    } else {
+      bf16* cp = reinterpret_cast<bf16*>(ep.C) + (long long)row * ep.ldc + col0;
+      if (full_chunk) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          if (ep.accumulate) {
+            const int4 old = *reinterpret_cast<const int4*>(cp + j);
+            float2 f;
+            f = unpack_bf16x2(old.x); v[j] += f.x; v[j + 1] += f.y;
+            f = unpack_bf16x2(old.y); v[j + 2] += f.x; v[j + 3] += f.y;
+            f = unpack_bf16x2(old.z); v[j + 4] += f.x; v[j + 5] += f.y;
+            f = unpack_bf16x2(old.w); v[j + 6] += f.x; v[j + 7] += f.y;
+          }
+          int4 o;
+          o.x = pack_bf16x2(v[j], v[j + 1]);
+          o.y = pack_bf16x2(v[j + 2], v[j + 3]);
+          o.z = pack_bf16x2(v[j + 4], v[j + 5]);
+          o.w = pack_bf16x2(v[j + 6], v[j + 7]);
+          *reinterpret_cast<int4*>(cp + j) = o;
+        }
+      } else {
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < N) {
+            float x = v[j];
+            if (ep.accumulate) x += __bfloat162float(cp[j]);
+            cp[j] = __float2bfloat16(x);
+          }
+      }
+    }
+}
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
@@ -217,153 +369,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * ep.alpha;
-        const bool full_chunk = (col0 + 32 <= N);
-
-        if (ep.epi == EPI_SWIGLU_BWD) {
-          // LlamaMLP backward fused into the down_proj dgrad: this thread owns d(act) for 32 intermediate
-          // channels of one token = two [16 gate | 16 up] blocks of the interleaved gate/up buffer.
-          if (row_ok) {
-            bf16* gp = ep.aux + (long long)row * ep.ld_aux + 2 * col0;
-            bf16* cp = reinterpret_cast<bf16*>(ep.C) + (long long)row * ep.ldc + col0;
-#pragma unroll
-            for (int blk = 0; blk < 2; ++blk) {
-              uint32_t og[8], ou[8], oa[8];
-#pragma unroll
-              for (int hv = 0; hv < 2; ++hv) {
-                const int4 graw = *reinterpret_cast<const int4*>(gp + blk * 32 + hv * 8);
-                const int4 uraw = *reinterpret_cast<const int4*>(gp + blk * 32 + 16 + hv * 8);
-                const uint32_t ug[4] = {(uint32_t)graw.x, (uint32_t)graw.y, (uint32_t)graw.z, (uint32_t)graw.w};
-                const uint32_t uu[4] = {(uint32_t)uraw.x, (uint32_t)uraw.y, (uint32_t)uraw.z, (uint32_t)uraw.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float2 g = unpack_bf16x2(ug[j]);
-                  const float2 u = unpack_bf16x2(uu[j]);
-                  const float d0 = v[blk * 16 + hv * 8 + 2 * j], d1 = v[blk * 16 + hv * 8 + 2 * j + 1];
-                  const float s0 = 1.f / (1.f + __expf(-g.x)), s1 = 1.f / (1.f + __expf(-g.y));
-                  const float a0 = g.x * s0, a1 = g.y * s1;
-                  oa[hv * 4 + j] = pack_bf16x2(a0 * u.x, a1 * u.y);
-                  og[hv * 4 + j] = pack_bf16x2(d0 * u.x * (s0 + a0 * (1.f - s0)), d1 * u.y * (s1 + a1 * (1.f - s1)));
-                  ou[hv * 4 + j] = pack_bf16x2(d0 * a0, d1 * a1);
-                }
-              }
-              *reinterpret_cast<int4*>(gp + blk * 32) = make_int4(og[0], og[1], og[2], og[3]);
-              *reinterpret_cast<int4*>(gp + blk * 32 + 8) = make_int4(og[4], og[5], og[6], og[7]);
-              *reinterpret_cast<int4*>(gp + blk * 32 + 16) = make_int4(ou[0], ou[1], ou[2], ou[3]);
-              *reinterpret_cast<int4*>(gp + blk * 32 + 24) = make_int4(ou[4], ou[5], ou[6], ou[7]);
-              *reinterpret_cast<int4*>(cp + blk * 16) = make_int4(oa[0], oa[1], oa[2], oa[3]);
-              *reinterpret_cast<int4*>(cp + blk * 16 + 8) = make_int4(oa[4], oa[5], oa[6], oa[7]);
-            }
-          }
-          continue;
-        }
-        if (ep.epi == EPI_SWIGLU) {
-          // chunk = 16 gate columns followed by their 16 up columns
-          if (row_ok) {
-            if (ep.aux != nullptr) {
-              bf16* ap = ep.aux + (long long)row * ep.ld_aux + col0;
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                int4 o;
-                o.x = pack_bf16x2(v[j], v[j + 1]);
-                o.y = pack_bf16x2(v[j + 2], v[j + 3]);
-                o.z = pack_bf16x2(v[j + 4], v[j + 5]);
-                o.w = pack_bf16x2(v[j + 6], v[j + 7]);
-                *reinterpret_cast<int4*>(ap + j) = o;
-              }
-            }
-            float o16[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) o16[j] = silu(v[j]) * v[16 + j];
-            bf16* cp = reinterpret_cast<bf16*>(ep.C) + (long long)row * ep.ldc + (col0 >> 1);
-#pragma unroll
-            for (int j = 0; j < 16; j += 8) {
-              int4 o;
-              o.x = pack_bf16x2(o16[j], o16[j + 1]);
-              o.y = pack_bf16x2(o16[j + 2], o16[j + 3]);
-              o.z = pack_bf16x2(o16[j + 4], o16[j + 5]);
-              o.w = pack_bf16x2(o16[j + 6], o16[j + 7]);
-              *reinterpret_cast<int4*>(cp + j) = o;
-            }
-          }
-          continue;
-        }
-
-        if (ep.epi == EPI_BIAS || ep.epi == EPI_BIAS_GELU_ERF || ep.epi == EPI_BIAS_GELU_TANH ||
-            ep.epi == EPI_BIAS_RESID) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (full_chunk || col0 + j < N) v[j] += __bfloat162float(__ldg(ep.bias + col0 + j));
-        }
-        if (ep.epi == EPI_BIAS_GELU_ERF) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-        } else if (ep.epi == EPI_BIAS_GELU_TANH) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
-        }
-        if (!row_ok) continue;  // lanes past M only take part in the TMEM load
-        if (ep.epi == EPI_RESID || ep.epi == EPI_BIAS_RESID) {
-          const bf16* rp = ep.resid + (long long)row * ep.ldr + col0;
-          if (full_chunk) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              const int4 rr = *reinterpret_cast<const int4*>(rp + j);
-              float2 f;
-              f = unpack_bf16x2(rr.x); v[j] += f.x; v[j + 1] += f.y;
-              f = unpack_bf16x2(rr.y); v[j + 2] += f.x; v[j + 3] += f.y;
-              f = unpack_bf16x2(rr.z); v[j + 4] += f.x; v[j + 5] += f.y;
-              f = unpack_bf16x2(rr.w); v[j + 6] += f.x; v[j + 7] += f.y;
-            }
-          } else {
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < N) v[j] += __bfloat162float(rp[j]);
-          }
-        }
-        if (ep.out_f32) {
-          float* cp = reinterpret_cast<float*>(ep.C) + (long long)row * ep.ldc + col0;
-          if (full_chunk) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-              if (ep.accumulate) {
-                const float4 old = *reinterpret_cast<const float4*>(cp + j);
-                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-              }
-              *reinterpret_cast<float4*>(cp + j) = o;
-            }
-          } else {
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < N) cp[j] = ep.accumulate ? cp[j] + v[j] : v[j];
-          }
-        } else {
-          bf16* cp = reinterpret_cast<bf16*>(ep.C) + (long long)row * ep.ldc + col0;
-          if (full_chunk) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (ep.accumulate) {
-                const int4 old = *reinterpret_cast<const int4*>(cp + j);
-                float2 f;
-                f = unpack_bf16x2(old.x); v[j] += f.x; v[j + 1] += f.y;
-                f = unpack_bf16x2(old.y); v[j + 2] += f.x; v[j + 3] += f.y;
-                f = unpack_bf16x2(old.z); v[j + 4] += f.x; v[j + 5] += f.y;
-                f = unpack_bf16x2(old.w); v[j + 6] += f.x; v[j + 7] += f.y;
-              }
-              int4 o;
-              o.x = pack_bf16x2(v[j], v[j + 1]);
-              o.y = pack_bf16x2(v[j + 2], v[j + 3]);
-              o.z = pack_bf16x2(v[j + 4], v[j + 5]);
-              o.w = pack_bf16x2(v[j + 6], v[j + 7]);
-              *reinterpret_cast<int4*>(cp + j) = o;
-            }
-          } else {
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < N) {
-                float x = v[j];
-                if (ep.accumulate) x += __bfloat162float(cp[j]);
-                cp[j] = __float2bfloat16(x);
-              }
-          }
-        }
+        epilogue_chunk(ep, v, row, row_ok, col0, N);
       }
       // all TMEM reads of this accumulator stage are complete (tcgen05.wait::ld above)
       tcgen05_fence_before();
@@ -378,6 +384,242 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   if (warp == 2) {
     tcgen05_fence_after();
     tmem_dealloc<C::kTmemCols>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 2-CTA variant (tcgen05 cta_group::2): a cluster of two CTAs on one TPC computes a 256 x 256 output tile.
+// Each CTA stages ITS 128 rows of A and ITS half (128 of 256 columns) of B; the leader CTA issues
+// tcgen05.mma.cta_group::2 (M=256) which reads B from both CTAs' shared memory, so every B byte is
+// loaded from L2 and read from smem once per pair instead of once per CTA (33 % less operand traffic per
+// flop: the train step is power-capped, energy per flop is what buys clocks). Accumulator rows live in
+// the TMEM of the CTA that owns them; barriers are per CTA at identical smem offsets:
+//   full[s]   (leader's)  count 2: leader arrive.expect_tx(both CTAs' bytes) + peer's remote arrive;
+//                         both CTAs' TMA loads complete_tx on the leader's barrier (peer bit masked)
+//   empty[s], tfull[a]    signalled in BOTH CTAs by the leader's multicast tcgen05.commit
+//   tempty[a] (leader's)  count 8: the four epilogue warps of both CTAs (peer warps arrive remotely)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n"
+      "}\n" ::"r"(bar),
+      "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t smem_dst, const void* tmap, uint32_t bar,
+                                                int32_t c_inner, int32_t c_outer) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar & 0xFEFFFFFFu), "r"(c_inner), "r"(c_outer)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ss_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                                 uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          bar),
+      "h"((uint16_t)3)
+      : "memory");
+}
+
+constexpr int BN2 = 256;             // cluster tile N
+constexpr int kStages2 = 6;
+constexpr int kA2Bytes = BM * BK * 2;          // this CTA's 128 rows of A
+constexpr int kB2Bytes = (BN2 / 2) * BK * 2;   // this CTA's 128 columns of B
+constexpr int kStage2Bytes = kA2Bytes + kB2Bytes;
+constexpr int kSmem2Bytes = kStages2 * kStage2Bytes + 1024 + 256;
+
+template <bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                         const __grid_constant__ CUtensorMap tmap_b, int M, int N, int K, int group_m,
+                         EpiParams ep) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + kStages2 * kStage2Bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages2 + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages2 + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages2 + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages2 + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int num_m = (M + 2 * BM - 1) / (2 * BM), num_n = (N + BN2 - 1) / BN2;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (K + BK - 1) / BK;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages2; ++s) {
+      mbar_init(full_bar(s), 2);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  auto tile_coords = [&](int t, int& m_blk, int& n_blk) {
+    const int per_group = group_m * num_n;
+    const int g = t / per_group;
+    const int first_m = g * group_m;
+    const int gsz = min(group_m, num_m - first_m);
+    const int r = t - g * per_group;
+    m_blk = first_m + (r % gsz);
+    n_blk = r / gsz;
+  };
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    int s = 0;
+    uint32_t phase = 0;
+    for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+      int m_blk, n_blk;
+      tile_coords(t, m_blk, n_blk);
+      const int m0 = m_blk * 2 * BM + (int)rank * BM;
+      const int n0 = n_blk * BN2 + (int)rank * (BN2 / 2);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(empty_bar(s), phase ^ 1);
+        const uint32_t sa = smem_base + s * kStage2Bytes;
+        const uint32_t sb = sa + kA2Bytes;
+        if (leader) mbar_arrive_expect_tx(full_bar(s), 2 * kStage2Bytes);
+        else mbar_arrive_remote(full_bar(s), 0);
+        const int k0 = kb * BK;
+        if constexpr (!A_MN) {
+          tma_load_2d_2sm(sa, &tmap_a, full_bar(s), k0, m0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BM / 64; ++j)
+            tma_load_2d_2sm(sa + j * (BK * 128), &tmap_a, full_bar(s), m0 + 64 * j, k0);
+        }
+        if constexpr (!B_MN) {
+          tma_load_2d_2sm(sb, &tmap_b, full_bar(s), k0, n0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN2 / 2 / 64; ++j)
+            tma_load_2d_2sm(sb + j * (BK * 128), &tmap_b, full_bar(s), n0 + 64 * j, k0);
+        }
+        if (++s == kStages2) { s = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0 && leader) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(A_MN) << 15) |
+                           (uint32_t(B_MN) << 16) | (uint32_t(BN2 >> 3) << 17) |
+                           (uint32_t((2 * BM) >> 4) << 24);
+    const uint64_t desc_a_base = make_desc_base(A_MN);
+    const uint64_t desc_b_base = make_desc_base(B_MN);
+    constexpr uint32_t a_kstep = A_MN ? (UMMA_K * 128) : (UMMA_K * 2);
+    constexpr uint32_t b_kstep = B_MN ? (UMMA_K * 128) : (UMMA_K * 2);
+    int s = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BN2;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full_bar(s), phase);
+        tcgen05_fence_after();
+        const uint32_t sa = smem_base + s * kStage2Bytes;
+        const uint32_t sb = sa + kA2Bytes;
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          const uint64_t da = desc_a_base | uint64_t(((sa + k * a_kstep) & 0x3FFFFu) >> 4);
+          const uint64_t db = desc_b_base | uint64_t(((sb + k * b_kstep) & 0x3FFFFu) >> 4);
+          umma_bf16_ss_2sm(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit_2sm(empty_bar(s));
+        if (kb == num_kb - 1) umma_commit_2sm(tfull_bar(acc));
+        if (++s == kStages2) { s = 0; phase ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue warps (both CTAs)
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+      int m_blk, n_blk;
+      tile_coords(t, m_blk, n_blk);
+      const int row = m_blk * 2 * BM + (int)rank * BM + q * 32 + lane;
+      const int n0 = n_blk * BN2;
+      const bool row_ok = row < M;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN2;
+#pragma unroll 1
+      for (int c = 0; c < BN2 / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= N) break;
+        __syncwarp();
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr + c * 32, r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * ep.alpha;
+        epilogue_chunk(ep, v, row, row_ok, col0, N);
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(tempty_bar(acc));
+        else mbar_arrive_remote(tempty_bar(acc), 0);
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tcgen05_fence_before();
+  cluster_sync_all();   // nobody may exit (or free TMEM) while the peer can still touch its smem / barriers
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
   }
 }
 
@@ -449,6 +691,27 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, co
   return MM_OK;
 }
 
+template <bool A_MN, bool B_MN>
+int launch2(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EpiParams& ep,
+            cudaStream_t stream) {
+  auto kern = gemm_tcgen05_2cta_kernel<A_MN, B_MN>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] {
+    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2Bytes);
+  });
+  MM_CHECK_CUDA(attr_err);
+  const int num_tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN2 - 1) / BN2);
+  int clusters = mm_num_sms() / 2;
+  if (clusters > num_tiles) clusters = num_tiles;
+  long long gm = (48ll << 20) / ((long long)2 * BM * K * 2);
+  if (gm < 2) gm = 2;
+  if (gm > 32) gm = 32;
+  kern<<<2 * clusters, kThreads, kSmem2Bytes, stream>>>(ta, tb, M, N, K, (int)gm, ep);
+  MM_CHECK_LAUNCH();
+  return MM_OK;
+}
+
 }  // namespace
 
 // See include/metamorph_b200.h for the contract.
@@ -484,6 +747,32 @@ MM_API int mm_gemm_bf16(const void* A, const void* B, void* C, const void* bias,
   }
   MM_CHECK_ARG(!(a_mn_major && !b_mn_major), "mm_gemm_bf16: (A MN-major, B K-major) not instantiated");
 
+  // The 2-CTA (cta_group::2, 256x256 cluster tile) kernel is the default for problems with at least one full
+  // wave of cluster tiles: measured on B200 it sustains more under the power cap (train step 845.8 ms vs
+  // 866-869 ms with the 1-CTA kernel on the same box, profiles/r01_gemm_2cta_ab.txt) although its burst rate is
+  // lower. force_bn == 512 forces it, force_bn 128/256 or MM_GEMM_2CTA=0 select the 1-CTA kernel.
+  static const bool env_2cta = !(getenv("MM_GEMM_2CTA") != nullptr && atoi(getenv("MM_GEMM_2CTA")) == 0);
+  const long long tiles2 = ceil_div64(M, 2 * BM) * ceil_div64(N, BN2);
+  const bool use_2cta = (force_bn == 512) || (force_bn == 0 && env_2cta && tiles2 >= mm_num_sms() / 2);
+  if (use_2cta) {
+    CUtensorMap ta2, tb2;
+    int rc2;
+    if (!a_mn_major) rc2 = make_tmap(&ta2, A, K, M, lda, BK, BM);
+    else             rc2 = make_tmap(&ta2, A, M, K, lda, 64, BK);
+    if (rc2) return rc2;
+    if (!b_mn_major) rc2 = make_tmap(&tb2, B, K, N, ldb, BK, BN2 / 2);
+    else             rc2 = make_tmap(&tb2, B, N, K, ldb, 64, BK);
+    if (rc2) return rc2;
+    EpiParams ep2;
+    ep2.C = C; ep2.ldc = ldc;
+    ep2.bias = reinterpret_cast<const bf16*>(bias);
+    ep2.resid = reinterpret_cast<const bf16*>(resid); ep2.ldr = ldr;
+    ep2.aux = reinterpret_cast<bf16*>(aux); ep2.ld_aux = ld_aux;
+    ep2.epi = epilogue; ep2.out_f32 = out_f32; ep2.accumulate = accumulate; ep2.alpha = alpha;
+    if (!a_mn_major && !b_mn_major) return launch2<false, false>(ta2, tb2, (int)M, (int)N, (int)K, ep2, stream);
+    if (!a_mn_major && b_mn_major) return launch2<false, true>(ta2, tb2, (int)M, (int)N, (int)K, ep2, stream);
+    return launch2<true, true>(ta2, tb2, (int)M, (int)N, (int)K, ep2, stream);
+  }
   int bn = 256;
   if (force_bn == 128 || force_bn == 256) {
     bn = force_bn;

@@ -27,7 +27,7 @@ def test_gemm_layouts(cuda_device, a_mn, b_mn, shape):
     a = torch.randn((K, M) if a_mn else (M, K), device=cuda_device).bfloat16()
     b = torch.randn((K, N) if b_mn else (N, K), device=cuda_device).bfloat16()
     ref = (a.float().t() if a_mn else a.float()) @ (b.float() if b_mn else b.float().t())
-    for bn in (128, 256):
+    for bn in (128, 256, 512):   # 512 = 2-CTA (cta_group::2) kernel
         out = ops.gemm(a, b, a_mn=a_mn, b_mn=b_mn, force_bn=bn)
         _close(out, ref, 1e-2, f"gemm bn={bn}")
 
