@@ -13,6 +13,13 @@
 //   decode_state  the per-sequence text/image mode state machine of greedy_decode
 //                 (metamorph_llama.py:547-582) on the device: no .item() host syncs.
 #include "common.cuh"
+#include <mutex>
+#include <stdlib.h>
+
+typedef CUresult (*PFN_encodeTiledSk)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                      CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                      CUtensorMapFloatOOBfill);
 
 namespace {
 
@@ -112,6 +119,133 @@ skinny_gemm_kernel(const bf16* __restrict__ x, long long ldx, const bf16* __rest
     if (epi == SK_RESID) s += __bfloat162float(resid[(long long)b * ldr + n]);
     if (out_f32) reinterpret_cast<float*>(y)[(long long)b * ldy + n] = s;
     else reinterpret_cast<bf16*>(y)[(long long)b * ldy + n] = __float2bfloat16(s);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// skinny GEMM v2: the weight slab is streamed by TMA into an 8-deep ring of 128B-swizzled tiles
+// ([ROWS rows x 256 k] per stage), so every CTA keeps 64-128 KB of HBM reads in flight without spending
+// registers on them; one producer lane + four consumer warps (2 k32-chunks each per stage, same
+// weight-slab-as-A-operand mma.sync trick as v1). Small-N projections (o_proj, down_proj) no longer pay
+// the load-wait-compute round trips of the register-staged kernel.
+constexpr int SK2_STAGES = 8;
+constexpr int SK2_KT = 256;      // k elements per stage
+constexpr int SK2_THREADS = 160; // warp 0 = TMA producer, warps 1..4 = consumers
+
+template <int ROWS>
+__global__ void __launch_bounds__(SK2_THREADS)
+skinny_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const bf16* __restrict__ x, long long ldx,
+                       void* __restrict__ y, long long ldy, const bf16* __restrict__ bias,
+                       const bf16* __restrict__ resid, long long ldr, int m, int N, int K, int epi, int out_f32) {
+  constexpr int G = ROWS / 16;
+  constexpr int BOX = ROWS * 128;              // bytes of one [ROWS x 64 k] TMA box
+  constexpr int STAGE = 4 * BOX;               // 4 boxes = 256 k
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar = base + SK2_STAGES * STAGE;
+  float* red = reinterpret_cast<float*>(base_ptr + SK2_STAGES * STAGE + 128);   // [4][ROWS][8]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * ROWS;
+  const int n_kt = (K + SK2_KT - 1) / SK2_KT;
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmap_w);
+    for (int s = 0; s < SK2_STAGES; ++s) {
+      mbar_init(bar + 8 * s, 1);                     // full
+      mbar_init(bar + 8 * (SK2_STAGES + s), 4);      // empty: one arrive per consumer warp
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kt = 0; kt < n_kt; ++kt) {
+        const int s = kt % SK2_STAGES;
+        const uint32_t ph = (uint32_t)((kt / SK2_STAGES) & 1);
+        mbar_wait(bar + 8 * (SK2_STAGES + s), ph ^ 1);
+        mbar_arrive_expect_tx(bar + 8 * s, STAGE);
+#pragma unroll
+        for (int bx = 0; bx < 4; ++bx)
+          tma_load_2d(base + s * STAGE + bx * BOX, &tmap_w, bar + 8 * s, kt * SK2_KT + bx * 64, n0);
+      }
+    }
+  } else {
+    const int cw = warp - 1;                 // consumer index 0..3
+    const int g = lane >> 2, t = lane & 3;
+    float acc[G][4];
+#pragma unroll
+    for (int i = 0; i < G; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const bf16* xrow = x + (long long)g * ldx;
+    const bool xok = g < m;
+    for (int kt = 0; kt < n_kt; ++kt) {
+      const int s = kt % SK2_STAGES;
+      const uint32_t ph = (uint32_t)((kt / SK2_STAGES) & 1);
+      // x fragments first (L1/L2 hits) so they overlap the barrier wait
+      int4 xb[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int k0 = kt * SK2_KT + (2 * cw + u) * 32 + t * 8;
+        xb[u] = (xok && k0 < K) ? *reinterpret_cast<const int4*>(xrow + k0) : make_int4(0, 0, 0, 0);
+      }
+      mbar_wait(bar + 8 * s, ph);
+      const uint8_t* st = base_ptr + s * STAGE;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int cc = 2 * cw + u;             // k32 chunk of this stage: box cc/2, half cc%2
+        const uint8_t* bx = st + (cc >> 1) * BOX;
+        const int chunk = (cc & 1) * 4 + t;    // 16-byte chunk index inside the 128-byte row
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+          const int r0 = i * 16 + g, r1 = r0 + 8;
+          const int4 w0 = *reinterpret_cast<const int4*>(bx + r0 * 128 + ((chunk ^ (r0 & 7)) << 4));
+          const int4 w1 = *reinterpret_cast<const int4*>(bx + r1 * 128 + ((chunk ^ (r1 & 7)) << 4));
+          const uint32_t a1[4] = {(uint32_t)w0.x, (uint32_t)w1.x, (uint32_t)w0.y, (uint32_t)w1.y};
+          const uint32_t a2[4] = {(uint32_t)w0.z, (uint32_t)w1.z, (uint32_t)w0.w, (uint32_t)w1.w};
+          mma_bf16_16816(acc[i], a1, (uint32_t)xb[u].x, (uint32_t)xb[u].y);
+          mma_bf16_16816(acc[i], a2, (uint32_t)xb[u].z, (uint32_t)xb[u].w);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar + 8 * (SK2_STAGES + s));
+    }
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+      red[(cw * ROWS + i * 16 + g) * 8 + 2 * t] = acc[i][0];
+      red[(cw * ROWS + i * 16 + g) * 8 + 2 * t + 1] = acc[i][1];
+      red[(cw * ROWS + i * 16 + g + 8) * 8 + 2 * t] = acc[i][2];
+      red[(cw * ROWS + i * 16 + g + 8) * 8 + 2 * t + 1] = acc[i][3];
+    }
+  }
+  __syncthreads();
+  if (epi == SK_SWIGLU) {
+    if (ROWS == 32 && threadIdx.x < 128) {
+      const int r = threadIdx.x >> 3, b = threadIdx.x & 7;
+      float gsum = 0.f, usum = 0.f;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        gsum += red[(w * ROWS + r) * 8 + b];
+        usum += red[(w * ROWS + r + 16) * 8 + b];
+      }
+      const int col = (n0 >> 1) + r;
+      if (b < m && n0 + r < N)
+        reinterpret_cast<bf16*>(y)[(long long)b * ldy + col] = __float2bfloat16(silu(gsum) * usum);
+    }
+    return;
+  }
+  for (int idx = threadIdx.x; idx < ROWS * 8; idx += SK2_THREADS) {
+    const int r = idx >> 3, b = idx & 7;
+    const int n = n0 + r;
+    if (b >= m || n >= N) continue;
+    float sacc = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) sacc += red[(w * ROWS + r) * 8 + b];
+    if (epi == SK_BIAS || epi == SK_BIAS_GELU) sacc += __bfloat162float(bias[n]);
+    if (epi == SK_BIAS_GELU) sacc = gelu_erf(sacc);
+    if (epi == SK_RESID) sacc += __bfloat162float(resid[(long long)b * ldr + n]);
+    if (out_f32) reinterpret_cast<float*>(y)[(long long)b * ldy + n] = sacc;
+    else reinterpret_cast<bf16*>(y)[(long long)b * ldy + n] = __float2bfloat16(sacc);
   }
 }
 
@@ -426,8 +560,57 @@ MM_API int mm_skinny_gemm(const void* x, const void* W, void* y, const void* bia
   MM_CHECK_ARG(epilogue >= SK_STORE && epilogue <= SK_SWIGLU, "mm_skinny_gemm: bad epilogue");
   MM_CHECK_ARG((epilogue != SK_BIAS && epilogue != SK_BIAS_GELU) || bias, "mm_skinny_gemm: bias missing");
   MM_CHECK_ARG(epilogue != SK_RESID || resid, "mm_skinny_gemm: residual missing");
-  const bool rows32 = (epilogue == SK_SWIGLU) || (N >= 32 * 2 * mm_num_sms());
+  const bool rows32 = (epilogue == SK_SWIGLU) || (N >= 32 * 4 * mm_num_sms());
   if (epilogue == SK_SWIGLU) MM_CHECK_ARG(N % 32 == 0 && !out_f32, "mm_skinny_gemm: SWIGLU needs N%%32==0");
+  static const bool use_v1 = getenv("MM_SKINNY_V1") != nullptr;
+  // measured on B200 (graph replay, profiles/r01_decode_skinny_gemm.txt): the TMA-pipelined kernel wins on the
+  // 16-row shapes (qkv 12.3 vs 14.8 us, o_proj 9.8 vs 13.8, down_proj 38.4 vs 42.8), the register-staged kernel
+  // on the 32-row ones (gate/up 55.1 vs 57.7, lm_head 182 vs 197)
+  if (!use_v1 && !rows32 && ((uintptr_t)W & 15) == 0) {
+    // TMA-pipelined kernel
+    static PFN_encodeTiledSk enc = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult q;
+      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+          q == cudaDriverEntryPointSuccess)
+        enc = reinterpret_cast<PFN_encodeTiledSk>(fn);
+    });
+    MM_CHECK_ARG(enc != nullptr, "mm_skinny_gemm: cuTensorMapEncodeTiled unavailable");
+    const int rows = rows32 ? 32 : 16;
+    CUtensorMap tm;
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
+    cuuint64_t strides[1] = {(cuuint64_t)ldw * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(W), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MM_CHECK_ARG(r == CUDA_SUCCESS, "mm_skinny_gemm: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    const int smem = SK2_STAGES * 4 * rows * 128 + 128 + 4 * rows * 8 * 4 + 1024;
+    if (rows32) {
+      static std::once_flag o32;
+      static cudaError_t e32 = cudaSuccess;
+      std::call_once(o32, [&] {
+        e32 = cudaFuncSetAttribute(skinny_gemm_tma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      });
+      MM_CHECK_CUDA(e32);
+      skinny_gemm_tma_kernel<32><<<(N + 31) / 32, SK2_THREADS, smem, stream>>>(
+          tm, (const bf16*)x, ldx, y, ldy, (const bf16*)bias, (const bf16*)resid, ldr, m, N, K, epilogue, out_f32);
+    } else {
+      static std::once_flag o16;
+      static cudaError_t e16 = cudaSuccess;
+      std::call_once(o16, [&] {
+        e16 = cudaFuncSetAttribute(skinny_gemm_tma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      });
+      MM_CHECK_CUDA(e16);
+      skinny_gemm_tma_kernel<16><<<(N + 15) / 16, SK2_THREADS, smem, stream>>>(
+          tm, (const bf16*)x, ldx, y, ldy, (const bf16*)bias, (const bf16*)resid, ldr, m, N, K, epilogue, out_f32);
+    }
+    MM_CHECK_LAUNCH();
+    return MM_OK;
+  }
   if (rows32)
     skinny_gemm_kernel<32><<<(N + 31) / 32, SK_THREADS, 0, stream>>>(
         (const bf16*)x, ldx, (const bf16*)W, ldw, y, ldy, (const bf16*)bias, (const bf16*)resid, ldr, m,
