@@ -232,6 +232,11 @@ def main():
         return 1
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # NCCL writes its banner ("NCCL version ...") to stdout when the communicator is created: keep stdout for the
+    # single JSON line by pointing fd 1 at stderr until the timed runs are done
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     from metamorph_b200 import ops, synthetic
@@ -343,6 +348,9 @@ def main():
         except Exception as e:  # noqa: BLE001 - secondary metric must not lose the headline line
             decode = {"error": repr(e)[:300]}
 
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -357,7 +365,8 @@ def main():
                            "lm_head_rows": "lm_head+CE run on the %d of %d rows that carry a label (identical loss/grads; "
                                            "algorithmic FLOPs below still count all rows)" % engine.hot.last_head_rows,
                            "loss": loss_val,
-                           "peak_hbm_gb": round(torch.cuda.max_memory_allocated() / 1e9, 1)},
+                           "peak_hbm_gb": round(torch.cuda.max_memory_allocated() / 1e9, 1),
+                           "peak_hbm_reserved_gb": round(torch.cuda.max_memory_reserved() / 1e9, 1)},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "decode": decode, "gpu_launches": launches, "clocks": clocks}
         print(json.dumps(line), flush=True)
     if world > 1:
