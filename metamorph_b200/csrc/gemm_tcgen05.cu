@@ -681,11 +681,15 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, co
   MM_CHECK_CUDA(attr_err);
   const int num_tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = num_tiles < mm_num_sms() ? num_tiles : mm_num_sms();
-  // A panel of a group ~ 48 MB of the 126 MB L2 (measured: the 16-row-block default re-read B 8x from HBM
-  // on the gate/up GEMM: 2.98 GB of DRAM traffic for 1.31 GB algorithmic, profiles/r01_gemm_ncu_summary.json)
-  long long gm = (48ll << 20) / ((long long)BM * K * 2);
-  if (gm < 4) gm = 4;
+  // Rasterisation group (row-blocks per group), from the DRAM-traffic sweep in profiles/r01_gemm_raster_sweep.txt:
+  //  * a wave of concurrently running tiles should be "square" in bytes (gm*A_slab ~ gn*B_slab) so that every
+  //    k-slab fetched from HBM is shared by as many tiles as possible (lock-step sharing through L2): 17 row-blocks;
+  //  * when K is short the A panel of a group (gm * BM * K * 2 bytes) can stay L2-resident across the whole sweep
+  //    over N, so B is streamed once per group: take up to 32 MB (64 MB panels thrash: 4.9 GB vs 1.1 GB of reads).
+  long long gm = (32ll << 20) / ((long long)BM * K * 2);
+  if (gm < 17) gm = 17;
   if (gm > 64) gm = 64;
+  if (const char* e = getenv("MM_GEMM_GM")) gm = atoi(e) > 0 ? atoi(e) : gm;   // rasterisation experiments
   kern<<<grid, kThreads, Cfg<BN>::kSmemBytes, stream>>>(ta, tb, M, N, K, (int)gm, ep);
   MM_CHECK_LAUNCH();
   return MM_OK;
@@ -704,9 +708,11 @@ int launch2(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, c
   const int num_tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN2 - 1) / BN2);
   int clusters = mm_num_sms() / 2;
   if (clusters > num_tiles) clusters = num_tiles;
-  long long gm = (48ll << 20) / ((long long)2 * BM * K * 2);
-  if (gm < 2) gm = 2;
+  // same rule as the 1-CTA launcher with 256-row blocks and 74 concurrent cluster tiles (square wave: 8 x 9)
+  long long gm = (32ll << 20) / ((long long)2 * BM * K * 2);
+  if (gm < 8) gm = 8;
   if (gm > 32) gm = 32;
+  if (const char* e = getenv("MM_GEMM_GM")) gm = atoi(e) > 0 ? atoi(e) : gm;   // rasterisation experiments
   kern<<<2 * clusters, kThreads, kSmem2Bytes, stream>>>(ta, tb, M, N, K, (int)gm, ep);
   MM_CHECK_LAUNCH();
   return MM_OK;
