@@ -34,6 +34,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=4, help="samples per GPU")
     ap.add_argument("--seq-len", type=int, default=4096)
+    ap.add_argument("--images-per-sample", type=int, default=4, help="half prompt-side, half answer-side")
     ap.add_argument("--layers", type=int, default=32, help="debug only: fewer layers => invalid as a result")
     ap.add_argument("--save-gu-layers", type=int, default=int(os.environ.get("MM_SAVE_GU_LAYERS", "32")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -250,7 +251,9 @@ def main():
     engine = TrainEngine(model, lr=6.93e-5, weight_decay=0.0, max_grad_norm=None, total_steps=1000,
                          n_save_gu_layers=min(args.save_gu_layers, args.layers))
     B, T = args.batch, args.seq_len
-    host_batch = synthetic.train_batch(B, T, seed=1234 + 1000 * rank)
+    host_batch = synthetic.train_batch(B, T, n_prompt_images=args.images_per_sample // 2,
+                                       n_answer_images=args.images_per_sample - args.images_per_sample // 2,
+                                       seed=1234 + 1000 * rank)
     n_images = host_batch["images"].shape[0]
     dev_batch = dict(host_batch)
     dev_batch["images"] = host_batch["images"].to(dev)

@@ -137,7 +137,8 @@ __global__ void __launch_bounds__(SK2_THREADS)
 skinny_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const bf16* __restrict__ x, long long ldx,
                        void* __restrict__ y, long long ldy, const bf16* __restrict__ bias,
                        const bf16* __restrict__ resid, long long ldr, int m, int N, int K, int epi, int out_f32) {
-  constexpr int G = ROWS / 16;
+  constexpr int G = ROWS >= 16 ? ROWS / 16 : 1;
+  constexpr bool HALF = ROWS == 8;             // 8-row slab: rows 8..15 of the MMA operand are zero
   constexpr int BOX = ROWS * 128;              // bytes of one [ROWS x 64 k] TMA box
   constexpr int STAGE = 4 * BOX;               // 4 boxes = 256 k
   extern __shared__ uint8_t smem_raw[];
@@ -200,7 +201,8 @@ skinny_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const bf16* _
         for (int i = 0; i < G; ++i) {
           const int r0 = i * 16 + g, r1 = r0 + 8;
           const int4 w0 = *reinterpret_cast<const int4*>(bx + r0 * 128 + ((chunk ^ (r0 & 7)) << 4));
-          const int4 w1 = *reinterpret_cast<const int4*>(bx + r1 * 128 + ((chunk ^ (r1 & 7)) << 4));
+          const int4 w1 = HALF ? make_int4(0, 0, 0, 0)
+                               : *reinterpret_cast<const int4*>(bx + r1 * 128 + ((chunk ^ (r1 & 7)) << 4));
           const uint32_t a1[4] = {(uint32_t)w0.x, (uint32_t)w1.x, (uint32_t)w0.y, (uint32_t)w1.y};
           const uint32_t a2[4] = {(uint32_t)w0.z, (uint32_t)w1.z, (uint32_t)w0.w, (uint32_t)w1.w};
           mma_bf16_16816(acc[i], a1, (uint32_t)xb[u].x, (uint32_t)xb[u].y);
@@ -214,8 +216,10 @@ skinny_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const bf16* _
     for (int i = 0; i < G; ++i) {
       red[(cw * ROWS + i * 16 + g) * 8 + 2 * t] = acc[i][0];
       red[(cw * ROWS + i * 16 + g) * 8 + 2 * t + 1] = acc[i][1];
-      red[(cw * ROWS + i * 16 + g + 8) * 8 + 2 * t] = acc[i][2];
-      red[(cw * ROWS + i * 16 + g + 8) * 8 + 2 * t + 1] = acc[i][3];
+      if (!HALF) {
+        red[(cw * ROWS + i * 16 + g + 8) * 8 + 2 * t] = acc[i][2];
+        red[(cw * ROWS + i * 16 + g + 8) * 8 + 2 * t + 1] = acc[i][3];
+      }
     }
   }
   __syncthreads();
@@ -578,7 +582,10 @@ MM_API int mm_skinny_gemm(const void* x, const void* W, void* y, const void* bia
         enc = reinterpret_cast<PFN_encodeTiledSk>(fn);
     });
     MM_CHECK_ARG(enc != nullptr, "mm_skinny_gemm: cuTensorMapEncodeTiled unavailable");
-    const int rows = rows32 ? 32 : 16;
+    static const int rows_override = getenv("MM_SKINNY_ROWS") ? atoi(getenv("MM_SKINNY_ROWS")) : 0;
+    int rows = rows32 ? 32 : 16;
+    // (an 8-row slab variant exists for experiments, MM_SKINNY_ROWS=8; measured slower: 13.4 vs 12.4 us on qkv)
+    if (rows_override == 8 || rows_override == 16) rows = rows_override;
     CUtensorMap tm;
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
     cuuint64_t strides[1] = {(cuuint64_t)ldw * 2};
@@ -597,6 +604,15 @@ MM_API int mm_skinny_gemm(const void* x, const void* W, void* y, const void* bia
       });
       MM_CHECK_CUDA(e32);
       skinny_gemm_tma_kernel<32><<<(N + 31) / 32, SK2_THREADS, smem, stream>>>(
+          tm, (const bf16*)x, ldx, y, ldy, (const bf16*)bias, (const bf16*)resid, ldr, m, N, K, epilogue, out_f32);
+    } else if (rows == 8) {
+      static std::once_flag o8;
+      static cudaError_t e8 = cudaSuccess;
+      std::call_once(o8, [&] {
+        e8 = cudaFuncSetAttribute(skinny_gemm_tma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      });
+      MM_CHECK_CUDA(e8);
+      skinny_gemm_tma_kernel<8><<<(N + 7) / 8, SK2_THREADS, smem, stream>>>(
           tm, (const bf16*)x, ldx, y, ldy, (const bf16*)bias, (const bf16*)resid, ldr, m, N, K, epilogue, out_f32);
     } else {
       static std::once_flag o16;
