@@ -678,7 +678,9 @@ flash_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + 7 * BT_TILE + 2048 + 88);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int jt = blockIdx.x, hk = blockIdx.y, b = blockIdx.z;
+  // grid = (Hkv*B, key tiles): CTAs are dispatched x-fastest, so ALL (head, batch) instances of the heaviest key
+  // tile (j = 0 sees every query tile) start first and the light tiles fill the tail (LPT-style schedule)
+  const int jt = blockIdx.y, hk = blockIdx.x % p.Hkv, b = blockIdx.x / p.Hkv;
   const int G = p.Hq / p.Hkv;
   const int kv0 = jt * 128;
   const int kv_len = p.seqlens ? p.seqlens[b] : p.T;
@@ -976,7 +978,7 @@ MM_API int mm_attn_bwd_tc(const void* q, const void* k, const void* v, const voi
     const char* e = getenv("MM_ATTN_DBG");
     p.dbg = e ? atoi(e) : 0;
   }
-  dim3 grid((T + 127) / 128, Hkv, B);
+  dim3 grid(Hkv * B, (T + 127) / 128);
   flash_bwd_tc_kernel<<<grid, BT_THREADS, BT_SMEM, stream>>>(tq, tk, tv, tdo, p);
   MM_CHECK_LAUNCH();
   return mm_attn_bwd_convert_launch(dq_accum, dq, (long long)B * T, Hq * 128, lddq, stream);
