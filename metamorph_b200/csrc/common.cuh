@@ -47,6 +47,14 @@ void mm_set_error(const char* fmt, ...);
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 int mm_num_sms();
+// programmatic dependent launch (PDL) for the decode chain: 1 unless MM_PDL=0 (api.cu)
+int mm_pdl_enabled();
+// experiment switches (MM_PDL_MODE bitmask, default 9 = GEMMs only, late trigger; B200 sweep of the 512-step decode:
+// off 4.586 ms/step, 1: 4.675, 3: 4.883, 9: 4.617 (4.495 with gate/up on the register-staged kernel), 11: 4.567 —
+// an early trigger lets the next GEMM's CTAs pile onto the first idle SMs and unbalances its weight stream): 1 = weight-streaming GEMMs launched with the PDL attribute,
+// 2 = the small decode kernels too, 4 = L2 prefetch in the register-staged GEMM prologue, 8 = trigger dependents
+// after the main loop instead of at kernel entry
+int mm_pdl_mode();
 int mm_attn_bwd_delta_launch(const void* o, const void* dout, float* delta, long long ldo, long long lddo,
                              int B, int T, int Hq, int head_dim, float delta_scale, const float* lse,
                              float* lse2, cudaStream_t stream);
@@ -57,6 +65,31 @@ int mm_attn_bwd_convert_launch(const float* dq_accum, void* dq, long long R, int
 // Device helpers
 // ----------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
+
+// Programmatic dependent launch. A kernel launched through launch_pdl may start while its stream predecessor is
+// still running (as soon as every predecessor CTA has executed griddep_launch or exited): everything before
+// griddep_wait() may only touch memory no earlier kernel writes (weights, tensor maps, barriers); griddep_wait()
+// returns once the predecessor grid has completed and flushed. Every kernel launched this way MUST execute
+// griddep_wait() (completion order along the chain is what makes buffer reuse two kernels back safe).
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(int allow, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                     cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = allow ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(SK_THREADS)
 skinny_gemm_kernel(const bf16* __restrict__ x, long long ldx, const bf16* __restrict__ W,
                    long long ldw, void* __restrict__ y, long long ldy, const bf16* __restrict__ bias,
                    const bf16* __restrict__ resid, long long ldr, int m, int N, int K, int epi,
-                   int out_f32) {
+                   int out_f32, int pdl) {
   constexpr int G = ROWS / 16;
   __shared__ float red[SK_THREADS / 32][ROWS][8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -47,6 +47,24 @@ skinny_gemm_kernel(const bf16* __restrict__ x, long long ldx, const bf16* __rest
   const bf16* xrow = x + (long long)g * ldx;  // batch row g (B operand column)
   const bool xok = g < m;
   const int nchunks = K >> 5;
+  if (!(pdl & 8)) griddep_launch();
+  if (pdl & 4) {  // PDL prologue: weights are never written by a kernel, so pull this lane's first chunks towards L2 while the
+     // producer of x is still running
+    constexpr int UNR0 = (G == 1) ? 4 : 2;
+#pragma unroll
+    for (int u = 0; u < UNR0; ++u) {
+      const int cc = warp + u * (SK_THREADS / 32);
+      if (cc < nchunks) {
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+          const int r0 = n0 + i * 16 + g, r1 = r0 + 8;
+          if (r0 < N) prefetch_l2(W + (long long)r0 * ldw + cc * 32 + t * 8);
+          if (r1 < N) prefetch_l2(W + (long long)r1 * ldw + cc * 32 + t * 8);
+        }
+      }
+    }
+  }
+  griddep_wait();
   // warp w handles k32-chunks w, w+8, ...; unrolled by UNR so that each lane keeps 2*G*UNR independent
   // 128-bit weight loads in flight (the kernel is a pure HBM stream: bytes in flight per SM set its rate)
   constexpr int UNR = (G == 1) ? 4 : 2;
@@ -82,6 +100,7 @@ skinny_gemm_kernel(const bf16* __restrict__ x, long long ldx, const bf16* __rest
       }
     }
   }
+  if (pdl & 8) griddep_launch();
   // acc[i]: c0,c1 = (row n = i*16+g, batch 2t,2t+1); c2,c3 = (row n+8, batch 2t,2t+1)
 #pragma unroll
   for (int i = 0; i < G; ++i) {
@@ -136,7 +155,8 @@ template <int ROWS>
 __global__ void __launch_bounds__(SK2_THREADS)
 skinny_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const bf16* __restrict__ x, long long ldx,
                        void* __restrict__ y, long long ldy, const bf16* __restrict__ bias,
-                       const bf16* __restrict__ resid, long long ldr, int m, int N, int K, int epi, int out_f32) {
+                       const bf16* __restrict__ resid, long long ldr, int m, int N, int K, int epi, int out_f32,
+                       int pdl) {
   constexpr int G = ROWS >= 16 ? ROWS / 16 : 1;
   constexpr bool HALF = ROWS == 8;             // 8-row slab: rows 8..15 of the MMA operand are zero
   constexpr int BOX = ROWS * 128;              // bytes of one [ROWS x 64 k] TMA box
@@ -157,9 +177,11 @@ skinny_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const bf16* _
     }
     fence_barrier_init();
   }
+  if (!(pdl & 8)) griddep_launch();
   __syncthreads();
   if (warp == 0) {
     if (lane == 0) {
+      // the producer does not wait for the previous kernel: the ring fills with weights while x is being produced
       for (int kt = 0; kt < n_kt; ++kt) {
         const int s = kt % SK2_STAGES;
         const uint32_t ph = (uint32_t)((kt / SK2_STAGES) & 1);
@@ -180,6 +202,7 @@ skinny_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const bf16* _
       for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     const bf16* xrow = x + (long long)g * ldx;
     const bool xok = g < m;
+    griddep_wait();                          // x (and later y/resid) belong to the previous kernel
     for (int kt = 0; kt < n_kt; ++kt) {
       const int s = kt % SK2_STAGES;
       const uint32_t ph = (uint32_t)((kt / SK2_STAGES) & 1);
@@ -222,7 +245,9 @@ skinny_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const bf16* _
       }
     }
   }
+  griddep_wait();
   __syncthreads();
+  if (pdl & 8) griddep_launch();
   if (epi == SK_SWIGLU) {
     if (ROWS == 32 && threadIdx.x < 128) {
       const int r = threadIdx.x >> 3, b = threadIdx.x & 7;
@@ -275,6 +300,8 @@ decode_attn_kernel(const bf16* __restrict__ qkv, long long ldqkv, bf16* __restri
   float* sred = svnew + DA_D;              // [8 warps][G][128] partial outputs
   float* sscore = sred + 8 * G * DA_D;     // [G][chunk_pad]
   const int hk = blockIdx.x, b = blockIdx.y, sp = blockIdx.z;
+  griddep_launch();
+  griddep_wait();
   const int pos = pos_arr[b];
   const int n_ctx = pos + 1;
   const int chunk = (n_ctx + S - 1) / S;
@@ -429,6 +456,8 @@ decode_attn_kernel(const bf16* __restrict__ qkv, long long ldqkv, bf16* __restri
 __global__ void decode_attn_combine_kernel(const float* __restrict__ part, bf16* __restrict__ out,
                                            long long ldo, int Hkv, int G, int S) {
   const int hk = blockIdx.x, b = blockIdx.y;
+  griddep_launch();
+  griddep_wait();
   const float* pin = part + (((long long)b * Hkv + hk) * S) * G * (2 + DA_D);
   for (int i = threadIdx.x; i < G * DA_D; i += blockDim.x) {
     const int h = i / DA_D, dcol = i % DA_D;
@@ -564,13 +593,17 @@ MM_API int mm_skinny_gemm(const void* x, const void* W, void* y, const void* bia
   MM_CHECK_ARG(epilogue >= SK_STORE && epilogue <= SK_SWIGLU, "mm_skinny_gemm: bad epilogue");
   MM_CHECK_ARG((epilogue != SK_BIAS && epilogue != SK_BIAS_GELU) || bias, "mm_skinny_gemm: bias missing");
   MM_CHECK_ARG(epilogue != SK_RESID || resid, "mm_skinny_gemm: residual missing");
+  const int pm = mm_pdl_mode();
   const bool rows32 = (epilogue == SK_SWIGLU) || (N >= 32 * 4 * mm_num_sms());
   if (epilogue == SK_SWIGLU) MM_CHECK_ARG(N % 32 == 0 && !out_f32, "mm_skinny_gemm: SWIGLU needs N%%32==0");
   static const bool use_v1 = getenv("MM_SKINNY_V1") != nullptr;
   // measured on B200 (graph replay, profiles/r01_decode_skinny_gemm.txt): the TMA-pipelined kernel wins on the
   // 16-row shapes (qkv 12.3 vs 14.8 us, o_proj 9.8 vs 13.8, down_proj 38.4 vs 42.8), the register-staged kernel
   // on the 32-row ones (gate/up 55.1 vs 57.7, lm_head 182 vs 197)
-  if (!use_v1 && !rows32 && ((uintptr_t)W & 15) == 0) {
+  // MM_SKINNY_GU_V2 moves the gate/up projection to the TMA kernel as well (measured slower, also under PDL)
+  static const bool gu_v2 = getenv("MM_SKINNY_GU_V2") != nullptr;
+  const bool v2_ok = !rows32 || (epilogue == SK_SWIGLU && gu_v2);
+  if (!use_v1 && v2_ok && ((uintptr_t)W & 15) == 0) {
     // TMA-pipelined kernel
     static PFN_encodeTiledSk enc = nullptr;
     static std::once_flag once;
@@ -603,8 +636,9 @@ MM_API int mm_skinny_gemm(const void* x, const void* W, void* y, const void* bia
         e32 = cudaFuncSetAttribute(skinny_gemm_tma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       });
       MM_CHECK_CUDA(e32);
-      skinny_gemm_tma_kernel<32><<<(N + 31) / 32, SK2_THREADS, smem, stream>>>(
-          tm, (const bf16*)x, ldx, y, ldy, (const bf16*)bias, (const bf16*)resid, ldr, m, N, K, epilogue, out_f32);
+      MM_CHECK_CUDA(launch_pdl(pm & 1, skinny_gemm_tma_kernel<32>, dim3((N + 31) / 32), dim3(SK2_THREADS), smem, stream, tm,
+                               (const bf16*)x, ldx, y, ldy, (const bf16*)bias, (const bf16*)resid, ldr, m, N, K,
+                               epilogue, out_f32, pm));
     } else if (rows == 8) {
       static std::once_flag o8;
       static cudaError_t e8 = cudaSuccess;
@@ -612,8 +646,9 @@ MM_API int mm_skinny_gemm(const void* x, const void* W, void* y, const void* bia
         e8 = cudaFuncSetAttribute(skinny_gemm_tma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       });
       MM_CHECK_CUDA(e8);
-      skinny_gemm_tma_kernel<8><<<(N + 7) / 8, SK2_THREADS, smem, stream>>>(
-          tm, (const bf16*)x, ldx, y, ldy, (const bf16*)bias, (const bf16*)resid, ldr, m, N, K, epilogue, out_f32);
+      MM_CHECK_CUDA(launch_pdl(pm & 1, skinny_gemm_tma_kernel<8>, dim3((N + 7) / 8), dim3(SK2_THREADS), smem, stream, tm,
+                               (const bf16*)x, ldx, y, ldy, (const bf16*)bias, (const bf16*)resid, ldr, m, N, K,
+                               epilogue, out_f32, pm));
     } else {
       static std::once_flag o16;
       static cudaError_t e16 = cudaSuccess;
@@ -621,20 +656,21 @@ MM_API int mm_skinny_gemm(const void* x, const void* W, void* y, const void* bia
         e16 = cudaFuncSetAttribute(skinny_gemm_tma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       });
       MM_CHECK_CUDA(e16);
-      skinny_gemm_tma_kernel<16><<<(N + 15) / 16, SK2_THREADS, smem, stream>>>(
-          tm, (const bf16*)x, ldx, y, ldy, (const bf16*)bias, (const bf16*)resid, ldr, m, N, K, epilogue, out_f32);
+      MM_CHECK_CUDA(launch_pdl(pm & 1, skinny_gemm_tma_kernel<16>, dim3((N + 15) / 16), dim3(SK2_THREADS), smem, stream, tm,
+                               (const bf16*)x, ldx, y, ldy, (const bf16*)bias, (const bf16*)resid, ldr, m, N, K,
+                               epilogue, out_f32, pm));
     }
     MM_CHECK_LAUNCH();
     return MM_OK;
   }
   if (rows32)
-    skinny_gemm_kernel<32><<<(N + 31) / 32, SK_THREADS, 0, stream>>>(
-        (const bf16*)x, ldx, (const bf16*)W, ldw, y, ldy, (const bf16*)bias, (const bf16*)resid, ldr, m,
-        N, K, epilogue, out_f32);
+    MM_CHECK_CUDA(launch_pdl(pm & 1, skinny_gemm_kernel<32>, dim3((N + 31) / 32), dim3(SK_THREADS), 0, stream, (const bf16*)x,
+                             ldx, (const bf16*)W, ldw, y, ldy, (const bf16*)bias, (const bf16*)resid, ldr, m, N, K,
+                             epilogue, out_f32, pm));
   else
-    skinny_gemm_kernel<16><<<(N + 15) / 16, SK_THREADS, 0, stream>>>(
-        (const bf16*)x, ldx, (const bf16*)W, ldw, y, ldy, (const bf16*)bias, (const bf16*)resid, ldr, m,
-        N, K, epilogue, out_f32);
+    MM_CHECK_CUDA(launch_pdl(pm & 1, skinny_gemm_kernel<16>, dim3((N + 15) / 16), dim3(SK_THREADS), 0, stream, (const bf16*)x,
+                             ldx, (const bf16*)W, ldw, y, ldy, (const bf16*)bias, (const bf16*)resid, ldr, m, N, K,
+                             epilogue, out_f32, pm));
   MM_CHECK_LAUNCH();
   return MM_OK;
 }
@@ -662,9 +698,9 @@ MM_API int mm_decode_attn(const void* qkv, long long ldqkv, void* kcache, void* 
     if (smem > 48 * 1024)                                                                                    \
       MM_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                          (int)smem));                                                        \
-    decode_attn_kernel<GG><<<grid, DA_THREADS, smem, stream>>>(                                              \
-        (const bf16*)qkv, ldqkv, (bf16*)kcache, (bf16*)vcache, pos, cos_t, sin_t, (float*)workspace, Hq, Hkv, \
-        Tmax, splits, scale);                                                                                \
+    MM_CHECK_CUDA(launch_pdl(mm_pdl_mode() & 2, decode_attn_kernel<GG>, grid, dim3(DA_THREADS), smem, stream, (const bf16*)qkv,  \
+                             ldqkv, (bf16*)kcache, (bf16*)vcache, pos, cos_t, sin_t, (float*)workspace, Hq,   \
+                             Hkv, Tmax, splits, scale));                                                     \
   } while (0)
   if (G == 1) MM_DA_LAUNCH(1);
   else if (G == 2) MM_DA_LAUNCH(2);
@@ -672,8 +708,8 @@ MM_API int mm_decode_attn(const void* qkv, long long ldqkv, void* kcache, void* 
   else MM_DA_LAUNCH(8);
 #undef MM_DA_LAUNCH
   MM_CHECK_LAUNCH();
-  decode_attn_combine_kernel<<<dim3(Hkv, B), 128, 0, stream>>>((const float*)workspace, (bf16*)out, ldo, Hkv, G,
-                                                               splits);
+  MM_CHECK_CUDA(launch_pdl(mm_pdl_mode() & 2, decode_attn_combine_kernel, dim3(Hkv, B), dim3(128), 0, stream, (const float*)workspace,
+                           (bf16*)out, ldo, Hkv, G, splits));
   MM_CHECK_LAUNCH();
   return MM_OK;
 }

@@ -16,6 +16,8 @@ rmsnorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16*
                    int M, int H, float eps) {
   __shared__ float red[32];
   const int nvec = H >> 3;
+  griddep_launch();
+  griddep_wait();
   for (int row = blockIdx.x; row < M; row += gridDim.x) {
     const bf16* xr = x + (size_t)row * H;
     float xv[kMaxVec][8];
@@ -259,8 +261,8 @@ MM_API int mm_rmsnorm_fwd(const void* x, const void* w, void* y, long long M, lo
                           cudaStream_t stream) {
   MM_CHECK_ARG(M > 0 && H > 0 && H % 8 == 0 && H <= 8 * kNormThreads * kMaxVec,
                "mm_rmsnorm_fwd: need H%%8==0 and H<=%d (H=%lld)", 8 * kNormThreads * kMaxVec, H);
-  rmsnorm_fwd_kernel<<<norm_grid((int)M), kNormThreads, 0, stream>>>(
-      (const bf16*)x, (const bf16*)w, (bf16*)y, (int)M, (int)H, eps);
+  MM_CHECK_CUDA(launch_pdl(mm_pdl_mode() & 2, rmsnorm_fwd_kernel, dim3(norm_grid((int)M)), dim3(kNormThreads), 0, stream, (const bf16*)x,
+                           (const bf16*)w, (bf16*)y, (int)M, (int)H, eps));
   MM_CHECK_LAUNCH();
   return MM_OK;
 }
