@@ -122,6 +122,23 @@ int mm_decode_attn(const void* qkv, long long ldqkv, void* kcache, void* vcache,
                    const float* cos_t, const float* sin_t, void* out, long long ldo, int B, int Hq, int Hkv,
                    int head_dim, int Tmax, float scale, void* workspace, long long workspace_bytes, int splits,
                    cudaStream_t s);
+/* Whole-stack decode step in one persistent kernel (csrc/decode_stack.cu): all L decoder layers of one KV-cached
+ * step (HF LlamaDecoderLayer x L as driven by greedy_decode, metamorph_llama.py:526-535) with a continuous TMA
+ * weight stream. plan_build fills a HOST buffer (tensor maps + norm pointers) that the caller copies to 128-byte
+ * aligned device memory; the workspace must be zero-filled once before the first step. x [B, hidden] is updated in
+ * place; K/V of the fed token are appended at pos[b]. Requires head_dim 128, hidden and heads*128 <= 4096, and
+ * hidden / intermediate multiples of 64. */
+long long mm_decode_stack_plan_bytes(int n_layers);
+int mm_decode_stack_plan_build(void* plan_host, int n_layers, const void* const* wqkv, const void* const* wo,
+                               const void* const* wgu, const void* const* wd, const void* const* ln1,
+                               const void* const* ln2, int hidden, int n_heads, int n_kv_heads, int head_dim,
+                               int intermediate);
+long long mm_decode_stack_workspace_bytes(int B, int hidden, int n_heads, int n_kv_heads, int intermediate);
+long long mm_decode_stack_trace_offset(int B, int hidden, int n_heads, int n_kv_heads, int intermediate);
+int mm_decode_stack(const void* plan_dev, int n_layers, void* x, void* kcache, void* vcache,
+                    long long cache_layer_stride, const int* pos, const float* cos_t, const float* sin_t, int B,
+                    int hidden, int n_heads, int n_kv_heads, int intermediate, int Tmax, float scale, float eps,
+                    void* workspace, long long workspace_bytes, cudaStream_t s);
 int mm_kv_prefill(const void* qkv, long long ld, void* kcache, void* vcache, int B, int T, int Hq, int Hkv,
                   int head_dim, int Tmax, cudaStream_t s);
 int mm_decode_state_step(int* in_image_mode, int* total_image_tokens, int* total_output, int* finished, int* pos,

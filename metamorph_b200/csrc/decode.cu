@@ -203,16 +203,29 @@ skinny_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const bf16* _
     const bf16* xrow = x + (long long)g * ldx;
     const bool xok = g < m;
     griddep_wait();                          // x (and later y/resid) belong to the previous kernel
-    for (int kt = 0; kt < n_kt; ++kt) {
-      const int s = kt % SK2_STAGES;
-      const uint32_t ph = (uint32_t)((kt / SK2_STAGES) & 1);
-      // x fragments first (L1/L2 hits) so they overlap the barrier wait
-      int4 xb[2];
+    // The x fragments come from L2: every lane streams exactly the fragments it feeds to its own MMAs through a
+    // private SK2_XP-deep cp.async ring in shared memory (register prefetching does not get deeper than ~1 stage:
+    // in-flight loads share a handful of scoreboards, so waiting for the oldest waits for the newest as well).
+    constexpr int SK2_XP = 2;
+    const uint32_t xring = base + SK2_STAGES * STAGE + 128 + 4 * ROWS * 8 * 4 + (threadIdx.x - 32) * 16;
+    uint8_t* xring_ptr = base_ptr + SK2_STAGES * STAGE + 128 + 4 * ROWS * 8 * 4 + (threadIdx.x - 32) * 16;
+    auto fetch_x = [&](int kt) {
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const int k0 = kt * SK2_KT + (2 * cw + u) * 32 + t * 8;
-        xb[u] = (xok && k0 < K) ? *reinterpret_cast<const int4*>(xrow + k0) : make_int4(0, 0, 0, 0);
+        const bool ok = xok && k0 < K;
+        cp_async16(xring + (kt % SK2_XP) * 4096 + u * 2048, ok ? (const void*)(xrow + k0) : (const void*)x, ok);
       }
+      cp_async_commit();
+    };
+#pragma unroll
+    for (int j = 0; j < SK2_XP; ++j) fetch_x(j);
+    for (int kt = 0; kt < n_kt; ++kt) {
+      const int s = kt % SK2_STAGES;
+      const uint32_t ph = (uint32_t)((kt / SK2_STAGES) & 1);
+      cp_async_wait<SK2_XP - 1>();
+      const uint8_t* xsrc = xring_ptr + (kt % SK2_XP) * 4096;
+      const int4 xb[2] = {*reinterpret_cast<const int4*>(xsrc), *reinterpret_cast<const int4*>(xsrc + 2048)};
       mbar_wait(bar + 8 * s, ph);
       const uint8_t* st = base_ptr + s * STAGE;
 #pragma unroll
@@ -234,7 +247,9 @@ skinny_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const bf16* _
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(bar + 8 * (SK2_STAGES + s));
+      fetch_x(kt + SK2_XP);
     }
+    cp_async_wait<0>();
 #pragma unroll
     for (int i = 0; i < G; ++i) {
       red[(cw * ROWS + i * 16 + g) * 8 + 2 * t] = acc[i][0];
@@ -628,7 +643,7 @@ MM_API int mm_skinny_gemm(const void* x, const void* W, void* y, const void* bia
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MM_CHECK_ARG(r == CUDA_SUCCESS, "mm_skinny_gemm: cuTensorMapEncodeTiled failed (%d)", (int)r);
-    const int smem = SK2_STAGES * 4 * rows * 128 + 128 + 4 * rows * 8 * 4 + 1024;
+    const int smem = SK2_STAGES * 4 * rows * 128 + 128 + 4 * rows * 8 * 4 + 2 * 4096 + 1024;
     if (rows32) {
       static std::once_flag o32;
       static cudaError_t e32 = cudaSuccess;

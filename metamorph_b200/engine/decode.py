@@ -8,6 +8,7 @@ only reset by <image_end>), but (a) with a KV cache instead of re-running the gr
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -21,6 +22,9 @@ class DecodeEngine:
     def __init__(self, model):
         self.m = model
         self.use_cuda_graph = True
+        # one persistent kernel for all decoder layers of a step (csrc/decode_stack.cu) when the shapes fit its
+        # envelope; MM_DECODE_STACK=0 (or use_stack_kernel=False) keeps the per-op kernels
+        self.use_stack_kernel = os.environ.get("MM_DECODE_STACK", "1") != "0"
 
     @torch.no_grad()
     def generate(self, inputs_embeds: torch.Tensor, prompt_lens: Optional[torch.Tensor] = None,
@@ -101,10 +105,18 @@ class DecodeEngine:
         ev[0].record()                                   # prefill done (enqueued) -> decode steps start
         heads_and_state(h_last, 0)
 
+        stack_plan = None
+        if self.use_stack_kernel and ops.decode_stack_supported(H, Hq, Hkv, dh, d.intermediate, B, Tmax):
+            stack_plan = ops.DecodeStackPlan(layers, H, Hq, Hkv, dh, d.intermediate, B, dev)
+        self.last_used_stack_kernel = stack_plan is not None
+        self.last_stack_plan = stack_plan
+
         def one_step_body():
             # position of the token being fed = pos - 1 (the state step already advanced pos)
             cur_pos = st["pos"] - 1
             x = xin
+            if stack_plan is not None:
+                return ops.decode_stack(stack_plan, x, kc, vc, cur_pos, stack.cos, stack.sin, stack.scale, d.rms_eps)
             for i, w in enumerate(layers):
                 n1 = ops.rmsnorm(x, w.ln1, d.rms_eps)
                 qkv = ops.skinny_gemm(n1, w.wqkv)

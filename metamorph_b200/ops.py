@@ -6,7 +6,7 @@ from typing import Optional
 
 import torch
 
-from ._lib import call, c_float, c_int, ll, ptr, require_cuda, stream_ptr
+from ._lib import c_float, c_int, c_void_p, call, ll, ptr, require_cuda, stream_ptr
 
 EPI_STORE, EPI_BIAS, EPI_BIAS_GELU_ERF, EPI_BIAS_GELU_TANH, EPI_RESID, EPI_BIAS_RESID, EPI_SWIGLU, EPI_SWIGLU_BWD = range(8)
 
@@ -364,6 +364,69 @@ def decode_attn(qkv, kcache, vcache, pos, cos, sin, Hq, Hkv, head_dim, scale, ou
          ptr(sin), ptr(out), ll(out.stride(0)), c_int(B), c_int(Hq), c_int(Hkv), c_int(head_dim),
          c_int(Tmax), c_float(scale), ptr(ws), ll(ws.numel()), c_int(splits), stream_ptr())
     return out
+
+
+class DecodeStackPlan:
+    """Device-resident launch plan of the one-kernel decode step (csrc/decode_stack.cu): TMA tensor maps of every
+    layer's four weight matrices + norm-weight pointers, and the zero-initialised activation / barrier workspace."""
+
+    def __init__(self, layers, hidden, n_heads, n_kv_heads, head_dim, intermediate, batch, device):
+        from ._lib import lib
+        L = len(layers)
+        fnb = lib().mm_decode_stack_plan_bytes
+        fnb.restype = ctypes_ll
+        nbytes = int(fnb(c_int(L)))
+        host = (_ctypes.c_uint8 * (nbytes + 128))()
+        base = _ctypes.addressof(host)
+        aligned = (base + 127) & ~127
+        arr_t = _ctypes.c_void_p * L
+
+        def arr(ts):
+            require_cuda(*ts)
+            for t in ts:
+                assert t.is_contiguous() and t.dtype == torch.bfloat16
+            return arr_t(*[t.data_ptr() for t in ts])
+
+        call("mm_decode_stack_plan_build", c_void_p(aligned), c_int(L), arr([w.wqkv for w in layers]),
+             arr([w.wo for w in layers]), arr([w.wgu for w in layers]), arr([w.wd for w in layers]),
+             arr([w.ln1 for w in layers]), arr([w.ln2 for w in layers]), c_int(hidden), c_int(n_heads),
+             c_int(n_kv_heads), c_int(head_dim), c_int(intermediate))
+        blob = torch.frombuffer(host, dtype=torch.uint8, count=nbytes, offset=aligned - base).clone()
+        self.plan = blob.to(device)
+        self._keep = layers                     # the plan holds raw pointers into these tensors
+        fnw = lib().mm_decode_stack_workspace_bytes
+        fnw.restype = ctypes_ll
+        wbytes = int(fnw(c_int(batch), c_int(hidden), c_int(n_heads), c_int(n_kv_heads), c_int(intermediate)))
+        self.workspace = torch.zeros(wbytes, dtype=torch.uint8, device=device)
+        self.dims = (L, hidden, n_heads, n_kv_heads, intermediate, batch)
+
+
+def decode_stack(plan: DecodeStackPlan, x, kcache, vcache, pos, cos, sin, scale, eps):
+    """One KV-cached decode step through all layers in one persistent kernel; x [B, H] is updated in place.
+    kcache / vcache: [L, B, Hkv, Tmax, 128]."""
+    require_cuda(x, kcache, vcache, pos, cos, sin)
+    L, H, Hq, Hkv, inter, batch = plan.dims
+    assert x.shape[0] == batch and x.is_contiguous() and kcache.is_contiguous() and vcache.is_contiguous()
+    call("mm_decode_stack", ptr(plan.plan), c_int(L), ptr(x), ptr(kcache), ptr(vcache), ll(kcache.stride(0)),
+         ptr(pos), ptr(cos), ptr(sin), c_int(batch), c_int(H), c_int(Hq), c_int(Hkv), c_int(inter),
+         c_int(kcache.shape[3]), c_float(scale), c_float(eps), ptr(plan.workspace), ll(plan.workspace.numel()),
+         stream_ptr())
+    return x
+
+
+def decode_stack_supported(hidden, n_heads, n_kv_heads, head_dim, intermediate, batch, t_max) -> bool:
+    """Shape envelope of the one-kernel step; outside it the engine uses the per-op CUDA kernels."""
+    if head_dim != 128 or hidden % 64 or intermediate % 64:
+        return False
+    if hidden > 4096 or n_heads * head_dim > 4096 or n_heads % n_kv_heads or batch > 8:
+        return False
+    g = n_heads // n_kv_heads
+    if g not in (1, 2, 4, 8):
+        return False
+    sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    splits = max(1, min(16, sms // (batch * n_kv_heads)))
+    cpad = ((t_max + splits - 1) // splits + 4) & ~3
+    return (g * 128 + 256 + 8 * g * 128 + 16 + g * cpad) * 4 <= 8 * (4096 * 2 + 64)
 
 
 def kv_prefill(qkv, kcache, vcache, B, T, Hq, Hkv, head_dim):
