@@ -13,8 +13,12 @@
 //   * phases per layer:  RMSNorm+QKV | RoPE + KV append + split-context attention (+ last-arriver combine) |
 //     o_proj + residual | RMSNorm + gate/up + SwiGLU | down_proj + residual, separated by grid barriers
 //     (monotonic counter, release/acquire at gpu scope);
-//   * tiles are dealt round-robin over the CTAs with the deal continuing across phases and layers, so the CTA that
-//     got an extra tile in one phase is not the one that gets it in the next.
+//   * tiles are dealt round-robin (tile j*SMs + cta) for the whole rounds; the tiles left over after the last whole
+//     round are shared stream-K style: their (subtile, k-stage) units are cut into one equal contiguous range per CTA,
+//     and a tile that straddles a range boundary is completed by the CTA holding its first stage from fp32 partial
+//     sums parked in the workspace (added in k order: deterministic). Every CTA streams the same number of weight
+//     bytes (+- one 16 KB stage) in every phase. (Stream-K over the WHOLE phase balances equally well but streams
+//     ~20 % slower on B200: 148 equally spaced contiguous ranges instead of a moving window of consecutive tiles.)
 // Activations between phases ([8, H] rows) live in an L2-resident workspace and are read with ld.global.cg.
 // The RMSNorm statistics reproduce rmsnorm_fwd_kernel's reduction order bit for bit.
 #include "common.cuh"
@@ -43,6 +47,7 @@ constexpr int DS_OFF_X = DS_NSTAGE * DS_STAGE;
 constexpr int DS_OFF_RED = DS_OFF_X + DS_XBYTES;
 constexpr int DS_OFF_MISC = DS_OFF_RED + DS_RED_BYTES;      // 64 floats of row statistics + flags
 constexpr int DS_OFF_BAR = DS_OFF_MISC + 512;
+constexpr int DS_SYNC_FLAGS = 384;           // word offset of the per-CTA partial-sum flags in the sync area
 constexpr int DS_SMEM = DS_OFF_BAR + 2 * DS_NSTAGE * 8 + 1024;
 
 struct DsParams {
@@ -56,12 +61,14 @@ struct DsParams {
   const int* pos;               // [B] index of the token being fed
   const float* cos_t;
   const float* sin_t;
-  unsigned* sync;               // [0] barrier arrivals, [1] exits, [32] barrier generation, [64 + b*Hkv + hk] combine
+  unsigned* sync;               // [0] barrier arrivals, [1] exits, [2] launch generation, [64 + b*Hkv + hk] combine
+                                // counters, [DS_SYNC_FLAGS + cta] stream-K partial flags
   bf16* qkv;                    // [8][(Hq+2Hkv)*128]
   bf16* attn;                   // [8][Hq*128]
   bf16* hmid;                   // [8][H]
   bf16* act;                    // [8][I]
   float* part;                  // [B][Hkv][S][G][2+128]
+  float* spart;                 // [SMs][2][128] stream-K partial sums (fp32)
   int L, B, H, Hq, Hkv, I, Tmax, S;
   float scale, eps;
   unsigned long long* trace;    // optional [L][16][nsm] globaltimer stamps (MM_DS_TRACE), else null
@@ -116,10 +123,6 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
-}
-
-__device__ __forceinline__ int first_tile(int cta, long long goff, int nsm) {
-  return (int)(((long long)cta + nsm - (goff % nsm)) % nsm);
 }
 
 // K is only required to be a multiple of 64: the last 512-wide stage is zero-filled by TMA on the weight side
@@ -460,32 +463,48 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const __gri
     // =================================================== producer ===========================================
     if (lane == 0) {
       // Two cursors walk the same flattened (layer, phase, tile, k-stage) schedule: `ld` issues the TMA loads into the
-      // ring as slots free up; `pf` can run p.pf_stages ahead issuing L2 tensor prefetches (MM_DS_PF). Measured on
-      // B200 the L2 run-ahead does not pay (512-step decode, ms/step: off 5.08, 8 stages 5.15, 16: 5.31, 32: 6.34),
-      // so it is off by default.
+      // ring as slots free up; `pf` runs p.pf_stages (MM_DS_PF, default 8) further ahead issuing L2 tensor prefetches,
+      // so HBM keeps streaming for a while when the ring is full (grid barriers, staging, attention). Measured on B200
+      // (512-step decode, ms/step): 0: 4.61, 4: 4.48, 8: 4.44, 12: 4.48, 16: 4.59, 24: 5.70 — a long run-ahead
+      // evicts its own lines before they are used.
+      // (all schedule arithmetic is 32-bit and incremental: a 64-bit division per stage on this single lane costs as
+      // much as the stage itself)
       struct Cursor {
-        int l, ph, t, s, ks;
-        long long goff;
+        int l, ph, j, nks;    // layer, phase, round (j < q: whole tile j*nsm+cta; j == q: stream-K share of the rest)
+        int st, ks, left;     // current subtile, k-stage within it, stage units left in the current range
         bool done;
       };
-      auto settle = [&](Cursor& c) {   // move to the first phase (from c.ph on) in which this CTA owns a tile
+      auto settle = [&](Cursor& c) {   // first non-empty range at or after (l, ph, j)
         while (!c.done) {
-          c.t = first_tile(cta, c.goff, nsm);
-          if (c.t < ntile[c.ph]) return;
-          c.goff += ntile[c.ph];
+          c.nks = (Kp[c.ph] + DS_KS - 1) / DS_KS;
+          const int TS = nsub[c.ph] * c.nks;
+          const int q = ntile[c.ph] / nsm;
+          if (c.j < q) {
+            c.st = (c.j * nsm + cta) * nsub[c.ph];
+            c.ks = 0;
+            c.left = TS;
+            return;
+          }
+          if (c.j == q) {
+            const int Ur = (ntile[c.ph] - q * nsm) * TS;
+            const int r0 = Ur * cta / nsm, r1 = Ur * (cta + 1) / nsm;
+            if (r0 < r1) {
+              c.st = q * nsm * nsub[c.ph] + r0 / c.nks;
+              c.ks = r0 % c.nks;
+              c.left = r1 - r0;
+              return;
+            }
+          }
+          c.j = 0;
           if (++c.ph == 4) { c.ph = 0; if (++c.l == p.L) c.done = true; }
         }
       };
       auto advance = [&](Cursor& c) {
-        const int nks = (Kp[c.ph] + DS_KS - 1) / DS_KS;
-        if (++c.ks < nks) return;
-        c.ks = 0;
-        if (++c.s < nsub[c.ph]) return;
-        c.s = 0;
-        c.t += nsm;
-        if (c.t < ntile[c.ph]) return;
-        c.goff += ntile[c.ph];
-        if (++c.ph == 4) { c.ph = 0; if (++c.l == p.L) { c.done = true; return; } }
+        if (--c.left > 0) {
+          if (++c.ks == c.nks) { c.ks = 0; ++c.st; }
+          return;
+        }
+        ++c.j;
         settle(c);
       };
       auto kv_prefetch = [&](int l) {
@@ -507,11 +526,11 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const __gri
       };
       auto prefetch_stage = [&](const Cursor& c) {
         const CUtensorMap* map = p.maps + c.l * 4 + c.ph;
-        const int row0 = (c.t * nsub[c.ph] + c.s) * 16;
+        const int row0 = c.st * 16, kblk = c.ks * 8;
         asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
-                     ::"l"(reinterpret_cast<uint64_t>(map)), "r"(0), "r"(row0), "r"(c.ks * 8) : "memory");
+                     ::"l"(reinterpret_cast<uint64_t>(map)), "r"(0), "r"(row0), "r"(kblk) : "memory");
       };
-      Cursor ld{0, 0, 0, 0, 0, 0, false}, pf{0, 0, 0, 0, 0, 0, false};
+      Cursor ld{0, 0, 0, 0, 0, 0, 0, false}, pf{0, 0, 0, 0, 0, 0, 0, false};
       settle(ld);
       settle(pf);
       int kv_layer = 0;
@@ -525,10 +544,10 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const __gri
         }
         const uint32_t slot = sc % DS_NSTAGE, par = (sc / DS_NSTAGE) & 1u;
         const CUtensorMap* map = p.maps + ld.l * 4 + ld.ph;
-        const int row0 = (ld.t * nsub[ld.ph] + ld.s) * 16;
+        const int row0 = ld.st * 16, kblk = ld.ks * 8;
         mbar_wait(bar_empty + 8 * slot, par ^ 1u);
         mbar_arrive_expect_tx(bar_full + 8 * slot, DS_STAGE);
-        tma_load_3d(base + slot * DS_STAGE, map, bar_full + 8 * slot, 0, row0, ld.ks * 8);
+        tma_load_3d(base + slot * DS_STAGE, map, bar_full + 8 * slot, 0, row0, kblk);
         ++sc;
         advance(ld);
         if (!pf.done) { prefetch_stage(pf); advance(pf); }
@@ -546,8 +565,9 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const __gri
   float* stat = reinterpret_cast<float*>(sbase + DS_OFF_MISC);
   int* flag = reinterpret_cast<int*>(sbase + DS_OFF_MISC + 256);
   uint32_t sc = 0;
-  long long goff = 0;
   unsigned bar_idx = 0;
+  // flags of this launch: generation (bumped by the last CTA to leave) x phases per launch; compared for equality
+  const unsigned epoch_base = ld_acquire_u32(p.sync + 2) * (unsigned)(4 * p.L + 1);
   int redbuf = 0;
   const int B = p.B;
 
@@ -569,10 +589,33 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const __gri
         else xg = (p.dbg & 32) ? nullptr : p.act;   // dbg 32: (wrong) fragments from shared memory, timing only
       }
       const int nks = (K + DS_KS - 1) / DS_KS;
-      float gate_keep = 0.f;
+      // Whole rounds of tiles, then a stream-K share of the rest: the rest's (subtile, k-stage) units are cut into nsm
+      // equal contiguous ranges. A tile whose units straddle a range boundary is finished by the CTA that holds its
+      // FIRST stage (it reaches that tile at the end of its range); the CTAs holding the later k-ranges reach it at
+      // the start of theirs, park their fp32 partial sums in the workspace and raise a flag. Partials are added in
+      // ascending-k order: deterministic.
+      const int TS = nsub[ph] * nks;
+      const int q = ntile[ph] / nsm;                       // whole rounds: tile j*nsm + cta (the access pattern that
+      const int base_u = q * nsm * TS;                     // streams fastest); only the rest is shared stream-K style
+      const int Ur = (ntile[ph] - q * nsm) * TS;
+      const unsigned epoch = epoch_base + (unsigned)(l * 4 + ph + 1);
       DS_TRACE(ph * 4 + 0);        // staged, tiles start
-      for (int t = first_tile(cta, goff, nsm); t < ntile[ph]; t += nsm) {
-        for (int s = 0; s < nsub[ph]; ++s) {
+      for (int j = 0; j <= q; ++j) {
+      int u, u1;
+      if (j < q) { u = (j * nsm + cta) * TS; u1 = u + TS; }
+      else { u = base_u + Ur * cta / nsm; u1 = base_u + Ur * (cta + 1) / nsm; }
+      while (u < u1) {
+        const int T = u / TS;
+        const int tile_end = (T + 1) * TS;
+        const int end = u1 < tile_end ? u1 : tile_end;
+        const bool head = (u == T * TS);
+        float sums[2] = {0.f, 0.f};
+        int uu = u;
+        while (uu < end) {
+          const int st = uu / nks, ks0 = uu % nks;
+          const int sub = st - T * nsub[ph];
+          const int sub_end = end < (st + 1) * nks ? end : (st + 1) * nks;
+          const int ks1 = ks0 + (sub_end - uu);
           float acc[4] = {0.f, 0.f, 0.f, 0.f};
           auto consume = [&](const int4 (&xb)[2]) {
             const uint32_t slot = sc % DS_NSTAGE, par = (sc / DS_NSTAGE) & 1u;
@@ -594,7 +637,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const __gri
             ++sc;
           };
           if (xg == nullptr) {
-            for (int ks = 0; ks < nks; ++ks) {
+            for (int ks = ks0; ks < ks1; ++ks) {
               const int kbase = (ks * DS_KS + cw * 64 + t4 * 8) & (DS_XMAXK - 1);   // (the mask only matters for dbg 32)
               const int4 xb[2] = {*reinterpret_cast<const int4*>(xs + g * DS_XSTRIDE + kbase * 2),
                                   *reinterpret_cast<const int4*>(xs + g * DS_XSTRIDE + (kbase + 32) * 2)};
@@ -612,14 +655,14 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const __gri
 #pragma unroll
               for (int c = 0; c < 2; ++c) {
                 const int k0 = ks * DS_KS + cw * 64 + t4 * 8 + c * 32;
-                const bool ok = (g < B && k0 < K);
+                const bool ok = (g < B && k0 < K && ks < ks1);
                 cp_async16(dst + c * 4096, ok ? (const void*)(xg + (size_t)g * K + k0) : (const void*)xg, ok);
               }
               cp_async_commit();
             };
 #pragma unroll
-            for (int j = 0; j < DS_XP; ++j) fetch_x(j);            // (stages past the end copy zeros: uniform groups)
-            for (int ks = 0; ks < nks; ++ks) {
+            for (int j = 0; j < DS_XP; ++j) fetch_x(ks0 + j);       // (stages past the end copy zeros: uniform groups)
+            for (int ks = ks0; ks < ks1; ++ks) {
               cp_async_wait<DS_XP - 1>();
               const uint8_t* src = xs + ctid * 16 + (ks % DS_XP) * 8192;
               const int4 xb[2] = {*reinterpret_cast<const int4*>(src), *reinterpret_cast<const int4*>(src + 4096)};
@@ -628,7 +671,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const __gri
             }
             cp_async_wait<0>();
           }
-          // ---- cross-warp reduction + epilogue
+          // ---- cross-warp reduction of this (part of a) subtile
           float* rb = red + redbuf * (8 * 16 * 8);
           redbuf ^= 1;
           rb[(cw * 16 + g) * 8 + 2 * t4] = acc[0];
@@ -638,24 +681,69 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const __gri
           cons_sync();
           if (ctid < 128) {
             const int r = ctid >> 3, b = ctid & 7;
-            float sum = 0.f;
+            float psum = 0.f;
 #pragma unroll
-            for (int w = 0; w < 8; ++w) sum += rb[(w * 16 + r) * 8 + b];
-            const int n = (t * nsub[ph] + s) * 16 + r;
-            if (ph == 0) {
-              if (b < B) p.qkv[(size_t)b * QKVN + n] = __float2bfloat16(sum);
-            } else if (ph == 1) {
-              if (b < B) p.hmid[(size_t)b * p.H + n] = __float2bfloat16(sum + ldcg_bf16(p.x + (size_t)b * p.H + n));
-            } else if (ph == 2) {
-              if (s == 0) gate_keep = sum;
-              else if (b < B) p.act[(size_t)b * p.I + t * 16 + r] = __float2bfloat16(silu(gate_keep) * sum);
-            } else {
-              if (b < B) p.x[(size_t)b * p.H + n] = __float2bfloat16(sum + ldcg_bf16(p.hmid + (size_t)b * p.H + n));
+            for (int w = 0; w < 8; ++w) psum += rb[(w * 16 + r) * 8 + b];
+            if (sub == 0) sums[0] = psum; else sums[1] = psum;
+          }
+          uu = sub_end;
+        }
+        bool finish = head;
+        if (!head) {
+          // later k-range of a tile owned by an earlier CTA: park the partial sums, raise the flag
+          if (ctid < 128) {
+            p.spart[(cta * 2 + 0) * 128 + ctid] = sums[0];
+            p.spart[(cta * 2 + 1) * 128 + ctid] = sums[1];
+          }
+          cons_sync();
+          if (ctid == 0)
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.sync + DS_SYNC_FLAGS + cta), "r"(epoch) : "memory");
+        } else if (end != tile_end) {
+          // owner of a tile whose later k-ranges belong to the next CTAs (c_first..c_last, possibly many when the
+          // rest is smaller than one stage per CTA): poll their flags in parallel, then add the partials in k order
+          const int c_first = cta + 1;
+          int c_last = c_first;
+          while (c_last + 1 < nsm && base_u + Ur * (c_last + 1) / nsm < tile_end) ++c_last;
+          for (int c2 = c_first + ctid; c2 <= c_last; c2 += DS_CONS) {
+            const int s2 = base_u + Ur * c2 / nsm, e2 = base_u + Ur * (c2 + 1) / nsm;
+            if (e2 > s2) {
+              const long long t0 = clock64();
+              while (ld_acquire_u32(p.sync + DS_SYNC_FLAGS + c2) != epoch) {
+                if (clock64() - t0 > (1ll << 32)) {
+                  printf("decode_stack: partial-sum flag timeout (block %d waits for %d)\n", cta, c2);
+                  __trap();
+                }
+              }
+            }
+          }
+          cons_sync();
+          if (ctid < 128) {
+#pragma unroll 4
+            for (int c2 = c_first; c2 <= c_last; ++c2) {
+              const int s2 = base_u + Ur * c2 / nsm, e2 = base_u + Ur * (c2 + 1) / nsm;
+              if (e2 > s2) {
+                sums[0] += __ldcg(p.spart + (c2 * 2 + 0) * 128 + ctid);
+                sums[1] += __ldcg(p.spart + (c2 * 2 + 1) * 128 + ctid);
+              }
             }
           }
         }
+        if (finish && ctid < 128) {
+          const int r = ctid >> 3, b = ctid & 7;
+          const int n = T * 16 + r;            // output feature (single-subtile phases) / SwiGLU channel (gate/up)
+          if (ph == 0) {
+            if (b < B) p.qkv[(size_t)b * QKVN + n] = __float2bfloat16(sums[0]);
+          } else if (ph == 1) {
+            if (b < B) p.hmid[(size_t)b * p.H + n] = __float2bfloat16(sums[0] + ldcg_bf16(p.x + (size_t)b * p.H + n));
+          } else if (ph == 2) {
+            if (b < B) p.act[(size_t)b * p.I + n] = __float2bfloat16(silu(sums[0]) * sums[1]);
+          } else {
+            if (b < B) p.x[(size_t)b * p.H + n] = __float2bfloat16(sums[0] + ldcg_bf16(p.hmid + (size_t)b * p.H + n));
+          }
+        }
+        u = end;
       }
-      goff += ntile[ph];
+      }   // rounds
       DS_TRACE(ph * 4 + 1);        // tiles done
       const bool last = (l == p.L - 1 && ph == 3);
       if (!last && !(p.dbg & 2)) grid_barrier(p.sync, ++bar_idx, (unsigned)nsm, ctid);
@@ -686,6 +774,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stack_kernel(const __gri
     if (old == (unsigned)nsm - 1) {
       p.sync[0] = 0u;
       p.sync[1] = 0u;
+      p.sync[2] = p.sync[2] + 1u;
       __threadfence();
     }
   }
@@ -707,18 +796,19 @@ PFN_encodeTiledDs ds_encoder() {
 inline long long align_up(long long v, long long a) { return (v + a - 1) / a * a; }
 
 struct DsWorkspace {
-  long long sync, qkv, attn, hmid, act, part, trace, total;
+  long long sync, qkv, attn, hmid, act, part, spart, trace, total;
 };
 constexpr int DS_TRACE_LAYERS = 64;
 DsWorkspace ds_workspace(int B, int H, int Hq, int Hkv, int I, int S) {
   DsWorkspace w;
   long long o = 0;
-  w.sync = o; o = align_up(o + (64 + 8 * Hkv) * 4, 256);
+  w.sync = o; o = align_up(o + (DS_SYNC_FLAGS + mm_num_sms()) * 4, 256);
   w.qkv = o;  o = align_up(o + 8ll * (Hq + 2 * Hkv) * DS_D * 2, 256);
   w.attn = o; o = align_up(o + 8ll * Hq * DS_D * 2, 256);
   w.hmid = o; o = align_up(o + 8ll * H * 2, 256);
   w.act = o;  o = align_up(o + 8ll * I * 2, 256);
   w.part = o; o = align_up(o + (long long)B * Hkv * S * (Hq / Hkv) * (2 + DS_D) * 4, 256);
+  w.spart = o; o = align_up(o + (long long)mm_num_sms() * 2 * 128 * 4, 256);
   w.trace = o; o = align_up(o + (long long)DS_TRACE_LAYERS * 16 * mm_num_sms() * 8, 256);
   w.total = o;
   return w;
@@ -807,6 +897,11 @@ MM_API int mm_decode_stack(const void* plan_dev, int n_layers, void* x, void* kc
   const int cpad = ((Tmax + S - 1) / S + 4) & ~3;
   MM_CHECK_ARG((long long)(G * DS_D + 2 * DS_D + 8 * G * DS_D + 16 + G * cpad) * 4 <= DS_XBYTES,
                "mm_decode_stack: context of %d positions does not fit the attention scratch", Tmax);
+  {  // the kernel's schedule arithmetic is 32-bit
+    const long long k512 = (intermediate + DS_KS - 1) / DS_KS;
+    const long long units = (long long)(intermediate / 16) * 2 * ((hidden + DS_KS - 1) / DS_KS) + (hidden / 16) * k512;
+    MM_CHECK_ARG(units * mm_num_sms() < (1ll << 30), "mm_decode_stack: shape too large for the 32-bit tile schedule");
+  }
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
@@ -832,11 +927,12 @@ MM_API int mm_decode_stack(const void* plan_dev, int n_layers, void* x, void* kc
   p.hmid = reinterpret_cast<bf16*>(w8 + ws.hmid);
   p.act = reinterpret_cast<bf16*>(w8 + ws.act);
   p.part = reinterpret_cast<float*>(w8 + ws.part);
+  p.spart = reinterpret_cast<float*>(w8 + ws.spart);
   p.L = n_layers; p.B = B; p.H = hidden; p.Hq = n_heads; p.Hkv = n_kv_heads; p.I = intermediate; p.Tmax = Tmax;
   p.S = S; p.scale = scale; p.eps = eps;
   static const int dbg = getenv("MM_DS_DBG") ? atoi(getenv("MM_DS_DBG")) : 0;
   p.dbg = dbg;
-  static const int pf_stages = getenv("MM_DS_PF") ? atoi(getenv("MM_DS_PF")) : 0;
+  static const int pf_stages = getenv("MM_DS_PF") ? atoi(getenv("MM_DS_PF")) : 8;
   p.pf_stages = pf_stages;
   static const bool trace = getenv("MM_DS_TRACE") != nullptr;
   p.trace = (trace && n_layers <= DS_TRACE_LAYERS) ? reinterpret_cast<unsigned long long*>(w8 + ws.trace) : nullptr;

@@ -22,9 +22,10 @@ class DecodeEngine:
     def __init__(self, model):
         self.m = model
         self.use_cuda_graph = True
-        # one persistent kernel for all decoder layers of a step (csrc/decode_stack.cu) when the shapes fit its
-        # envelope; MM_DECODE_STACK=0 (or use_stack_kernel=False) keeps the per-op kernels
-        self.use_stack_kernel = os.environ.get("MM_DECODE_STACK", "1") != "0"
+        # Opt-in (MM_DECODE_STACK=1 / use_stack_kernel=True): one persistent kernel for all decoder layers of a step
+        # (csrc/decode_stack.cu). Parity-tested, but on B200 it does not beat the per-op kernels yet (4.44 vs 4.27
+        # ms/step on the 512-position batch-8 decode, profiles/r01_decode_stack_kernel.txt), so they stay the default.
+        self.use_stack_kernel = os.environ.get("MM_DECODE_STACK", "0") == "1"
 
     @torch.no_grad()
     def generate(self, inputs_embeds: torch.Tensor, prompt_lens: Optional[torch.Tensor] = None,

@@ -176,3 +176,31 @@ def test_decode_stack_kernel_matches_per_op_step(cuda_device, dims):
         kc_a.copy_(kc_b); vc_a.copy_(vc_b)
     sync_words = plan.workspace[:8].view(torch.int32)
     assert int(sync_words[0]) == 0 and int(sync_words[1]) == 0, "barrier counters must be re-armed"
+
+
+def test_engine_with_stack_kernel_matches_default_path(cuda_device):
+    """DecodeEngine with the opt-in one-kernel decoder stack must emit the same ids (teacher-forced schedule) and
+    the same visual embeddings (bf16 tolerance) as the default per-op step, CUDA graph replay included."""
+    from oracle.weights import TINY, make_weights
+    from tests.helpers import build_product_model
+    model = build_product_model(TINY, make_weights(TINY), num_image_tokens=4)
+    model.eval()
+    g = torch.Generator().manual_seed(11)
+    B, P, steps = 3, 9, 16
+    prompts = torch.randint(0, 128000, (B, P), generator=g)
+    forced = torch.randint(0, 128000, (B, steps + 2), generator=g).to(torch.int32)
+    forced[0, 1] = 128256; forced[0, 8] = 128257
+    forced[1, 5] = 128256
+    emb = model.get_model().embed_tokens(prompts.cuda())
+    outs = {}
+    for use_stack in (False, True):
+        model._decode.use_stack_kernel = use_stack
+        outs[use_stack] = model.greedy_decode(None, None, emb, max_new_tokens=steps - 1, output_image=True,
+                                              forced_tokens=forced)
+        assert model._decode.last_used_stack_kernel == use_stack
+    model._decode.use_stack_kernel = False
+    for b in range(B):
+        assert outs[True][0][b].cpu().tolist() == outs[False][0][b].cpu().tolist()
+        assert outs[True][1][b].shape == outs[False][1][b].shape
+        if outs[True][1][b].shape[0]:
+            _close(outs[True][1][b], outs[False][1][b], 3e-2, f"image embeds seq {b}")
