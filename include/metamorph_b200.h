@@ -113,6 +113,19 @@ int mm_attn_bwd(const void* q, const void* k, const void* v, const void* o, cons
                 int Hq, int Hkv, int head_dim, float scale, void* workspace, long long workspace_bytes,
                 cudaStream_t s);
 
+/* On-GPU SigLIP image pre-processing, bit-exact with the reference's CPU chain:
+ * expand2square + processor.preprocess (metamorph/train/train.py:1189-1209) with the SigLIP processor of
+ * multimodal_encoder/siglip_encoder.py:113-121 = Pillow BICUBIC resize (ImagingResample: two uint8 passes, 22-bit
+ * fixed-point coefficients) + x 1/255 + normalise 0.5/0.5 + channels first.
+ * mm_resize_coeff_build is a HOST function (no CUDA): it fills a host buffer with the coefficient table of one axis;
+ * the caller copies it to the device. mm_siglip_preprocess: img uint8 [H][W][3], tmp uint8 [rows][out][3] scratch
+ * (rows = padded side, or H), lut = 256 floats, out = [3][out][out] fp32 (or bf16). */
+long long mm_resize_coeff_bytes(int in_size, int out_size);
+int mm_resize_coeff_build(void* host_buf, int in_size, int out_size);
+int mm_siglip_preprocess(const void* img, int H, int W, int pad_square, int fill, const void* coeff_x,
+                         const void* coeff_y, int ksize_x, int ksize_y, int out_size, const float* lut, void* tmp,
+                         void* out, int out_bf16, cudaStream_t s);
+
 /* KV-cached decode step (replaces the no-cache loop of greedy_decode, metamorph_llama.py:502-597). */
 int mm_skinny_gemm(const void* x, const void* W, void* y, const void* bias, const void* resid, long long ldx,
                    long long ldw, long long ldy, long long ldr, int m, int N, int K, int epilogue, int out_f32,

@@ -228,8 +228,8 @@ class HotPath:
         if len(plan.target_image_idx) == n_img:
             targets = feats
         else:
-            tidx = torch.tensor(plan.target_image_idx, dtype=torch.long).to(feats.device, non_blocking=True)
-            targets = feats.index_select(0, tidx)
+            tidx = torch.tensor(plan.target_image_idx, dtype=torch.int32).to(feats.device, non_blocking=True)
+            targets = ops.gather_rows(feats.reshape(n_img, -1).contiguous(), tidx).view(-1, *feats.shape[1:])
         row_map = plan.row_map.reshape(-1).to(dev, non_blocking=True)
         x = ops.interleave_gather(model.embed_tokens.weight.data, ar_feats, row_map)
         pos = plan.position_ids.reshape(-1).to(torch.int32).to(dev, non_blocking=True)
