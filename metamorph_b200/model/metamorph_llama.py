@@ -222,7 +222,14 @@ class MetaMorphLlamaForCausalLM(nn.Module, MetaMorphMetaForCausalLM):
                 sd.pop(k)
         return super().load_state_dict(sd, strict=strict)
 
-    def save_pretrained(self, save_directory: str, state_dict=None, **kwargs):
+    def save_pretrained(self, save_directory: str, state_dict=None, max_shard_size="5GB", safe_serialization=True,
+                        **kwargs):
+        """HF layout, as the reference's `trainer._save` leaves it (train.py:213-222): config.json + (sharded)
+        safetensors under the reference's parameter names, streamed tensor by tensor from the fused device layout."""
+        from .. import checkpoint
+        if state_dict is None and safe_serialization:
+            checkpoint.save_model(self, save_directory, max_shard_size=max_shard_size)
+            return
         os.makedirs(save_directory, exist_ok=True)
         self.config.save_pretrained(save_directory)
         sd = state_dict if state_dict is not None else self.state_dict()

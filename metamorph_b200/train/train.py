@@ -69,6 +69,7 @@ class TrainingArguments:
     seed: int = field(default=42)
     gradient_checkpointing: bool = field(default=True)  # accepted for CLI compatibility; selective recompute is built in
     save_gu_layers: int = field(default=32)
+    save_steps: int = field(default=0)          # > 0: write output_dir/checkpoint-<step> every save_steps steps
 
 
 def rank0_print(*args):
@@ -149,7 +150,15 @@ def train(attn_implementation=None, data_module_factory: Optional[Callable[..., 
             "the reference's JSONL/image dataset pipeline (train.py LazySupervisedDataset) is host-side code "
             "outside the hot path; pass data_module_factory=... or --data_path synthetic")
     model.train()
-    for step in range(training_args.max_steps):
+    from .. import checkpoint
+    start = 0
+    resume = checkpoint.latest_checkpoint(training_args.output_dir) if training_args.output_dir else None
+    if resume is not None:                                    # train.py:1592-1595: checkpoint-* present -> resume
+        start = checkpoint.load_training_checkpoint(engine, resume)
+        rank0_print(f"resumed from {resume} at step {start}")
+        for _ in range(start):                                # keep the data stream aligned with the step counter
+            next(batches)
+    for step in range(start, training_args.max_steps):
         out = engine.step(next(batches))
         if (step + 1) % training_args.logging_steps == 0:
             vals = torch.cat([out["loss"].reshape(1), out["loss_language"].reshape(1), out["loss_image_ar"].reshape(1)])
@@ -159,8 +168,21 @@ def train(attn_implementation=None, data_module_factory: Optional[Callable[..., 
             l, ll_, li = vals.tolist()
             model.loss_language, model.loss_image_ar = ll_, li
             rank0_print(f"step {step + 1}: loss {l:.4f} loss_language {ll_:.4f} loss_image_ar {li:.4f} lr {engine.current_lr:.3e}")
+        if training_args.save_steps > 0 and (step + 1) % training_args.save_steps == 0 and rank == 0 \
+                and training_args.output_dir:
+            torch.cuda.synchronize()
+            if model_args.tune_mm_mlp_adapter:                # metamorph_trainer.py:273-291
+                checkpoint.save_mm_projector_checkpoint(model, training_args.output_dir, step + 1,
+                                                        use_im_start_end=model_args.mm_use_im_start_end)
+            else:
+                checkpoint.save_training_checkpoint(engine, training_args.output_dir)
     if rank == 0 and training_args.output_dir:
-        model.save_pretrained(training_args.output_dir)
+        torch.cuda.synchronize()
+        if model_args.tune_mm_mlp_adapter:                    # safe_save_model_for_hf_trainer, train.py:189-207
+            checkpoint.save_mm_projector(model, training_args.output_dir,
+                                         use_im_start_end=model_args.mm_use_im_start_end)
+        else:
+            model.save_pretrained(training_args.output_dir)
     return model
 
 

@@ -17,8 +17,8 @@ os.environ.setdefault("WANDB_MODE", "disabled")
 os.environ.setdefault("TRANSFORMERS_OFFLINE", "1")
 sys.dont_write_bytecode = True
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, "/root/reference")
 sys.path.insert(0, REPO)
+sys.path.insert(0, "/root/reference")   # first: `metamorph` must be the reference, not this repo's alias package
 
 from oracle.weights import TINY, make_batch, make_weights  # noqa: E402
 

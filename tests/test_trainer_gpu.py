@@ -84,3 +84,37 @@ def test_loss_decreases_over_steps(cuda_device):
     eng = TrainEngine(m, lr=2e-3, constant_lr=True)
     losses = [float(eng.step(_batch())["loss"]) for _ in range(6)]
     assert losses[-1] < losses[0] - 0.5, losses
+
+
+def test_training_checkpoint_resume(cuda_device, tmp_path):
+    """`checkpoint-N` (HF-format weights + optimizer fp32 master/m/v + trainer_state.json) restores
+    the engine exactly, and the resumed run tracks the uninterrupted one (the backward uses fp32 atomics, so the
+    continuation is compared at bf16 tolerance, the restored state bit for bit)."""
+    from metamorph_b200 import checkpoint as ck
+    from metamorph_b200.engine.trainer import TrainEngine
+    W = make_weights(TINY)
+    m_a = build_product_model(TINY, W)
+    e_a = TrainEngine(m_a, lr=1e-3, total_steps=10, warmup_ratio=0.2)
+    for _ in range(2):
+        e_a.step(_batch())
+    torch.cuda.synchronize()
+    ckpt = ck.save_training_checkpoint(e_a, str(tmp_path), max_shard_size="40MB")
+    assert ckpt.endswith("checkpoint-2") and ck.latest_checkpoint(str(tmp_path)) == ckpt
+    saved = {n: (st.p32.clone(), st.m.clone(), st.v.clone(), st.p16.clone()) for n, st in e_a.opt.items()}
+    losses_a = [float(e_a.step(_batch())["loss"]) for _ in range(2)]
+
+    m_b = build_product_model(TINY, make_weights(TINY, seed=123))       # different weights: everything must come from disk
+    e_b = TrainEngine(m_b, lr=1e-3, total_steps=10, warmup_ratio=0.2)
+    assert ck.load_training_checkpoint(e_b, ckpt) == 2 and e_b.step_count == 2
+    for n, st in e_b.opt.items():
+        p32, m, v, p16 = saved[n]
+        assert torch.equal(st.p32, p32) and torch.equal(st.m, m) and torch.equal(st.v, v) and torch.equal(st.p16, p16), n
+    from metamorph_b200.engine.trainer import cosine_lr
+    assert e_b.current_lr == cosine_lr(2, 10, 1e-3, 0.2)                # schedule position follows the step counter
+    losses_b = [float(e_b.step(_batch())["loss"]) for _ in range(2)]
+    for la, lb in zip(losses_a, losses_b):
+        assert abs(la - lb) <= 2e-3 * abs(la) + 1e-3, (losses_a, losses_b)
+    pa, pb = _params(m_a), _params(m_b)
+    for n in pa:
+        err = (pa[n] - pb[n]).abs().max().item()
+        assert err <= 2e-2 * (pa[n].abs().max().item() + 1e-3), n
