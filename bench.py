@@ -300,6 +300,20 @@ def main():
     from metamorph_b200.engine.trainer import TrainEngine
     call("mm_check_device")
 
+    # SURVEY section 8f N1, measured before the 8 B model and its optimizer state fill the HBM
+    preprocess = None
+    if rank == 0 and world == 1 and not args.no_decode:
+        try:
+            pk = {}
+            try:
+                with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                    pk = json.load(f)
+            except Exception:  # noqa: BLE001
+                pass
+            preprocess = preprocess_bench(dev, pk)
+        except Exception as e:  # noqa: BLE001
+            preprocess = {"error": repr(e)[:300]}
+
     torch.manual_seed(0)
     cfg = synthetic.make_config(llama=dict(num_hidden_layers=args.layers), max_len=args.seq_len)
     model = synthetic.build_model(cfg, device=dev)
@@ -405,13 +419,6 @@ def main():
             decode = decode_bench(model, dev, peaks)
         except Exception as e:  # noqa: BLE001 - secondary metric must not lose the headline line
             decode = {"error": repr(e)[:300]}
-
-    preprocess = None
-    if rank == 0 and world == 1 and not args.no_decode:
-        try:
-            preprocess = preprocess_bench(dev, peaks)
-        except Exception as e:  # noqa: BLE001
-            preprocess = {"error": repr(e)[:300]}
 
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)

@@ -97,12 +97,14 @@ class SiglipGpuImageProcessor:
              ptr(cx), ptr(cy), c_int(kx), c_int(ky), c_int(self.out_size), ptr(self._lut), ptr(self._tmp), ptr(out),
              c_int(1 if out.dtype == torch.bfloat16 else 0), stream_ptr())
 
-    def preprocess(self, images, return_tensors="pt", **_):
+    def preprocess(self, images, return_tensors="pt", out=None, **_):
         """images: one image or a list (PIL / numpy HWC uint8 / uint8 tensors, host or device).
-        Returns {'pixel_values': [N, 3, S, S]} on the device, like `processor.preprocess(...)`."""
+        Returns {'pixel_values': [N, 3, S, S]} on the device, like `processor.preprocess(...)`; `out` lets the caller
+        supply the destination (no allocation on the hot path)."""
         if not isinstance(images, (list, tuple)):
             images = [images]
-        out = torch.empty((len(images), 3, self.out_size, self.out_size), dtype=self.out_dtype, device=self.device)
+        if out is None:
+            out = torch.empty((len(images), 3, self.out_size, self.out_size), dtype=self.out_dtype, device=self.device)
         for i, im in enumerate(images):
             t = _as_hwc_u8(im)
             if not t.is_cuda:
@@ -123,7 +125,8 @@ class ImageBatchPipeline:
         self.stream = torch.cuda.Stream(device=processor.device)
         self.host = [torch.empty(max_bytes, dtype=torch.uint8).pin_memory() for _ in range(2)]
         self.dev = [torch.empty(max_bytes, dtype=torch.uint8, device=processor.device) for _ in range(2)]
-        self.slot = 0
+        self.out = [None, None]          # per-slot outputs, kept across batches: a training process that fills HBM must
+        self.slot = 0                    # not go back to the allocator every step
         self.pending = None
         self.h2d_bytes = 0
 
@@ -143,7 +146,13 @@ class ImageBatchPipeline:
         self.stream.wait_stream(torch.cuda.current_stream())     # the slot's previous consumer has been enqueued
         with torch.cuda.stream(self.stream):
             dev[:total].copy_(host[:total], non_blocking=True)
-            out = self.p.preprocess([dev[o:o + h * w * 3].view(h, w, 3) for o, (h, w, _) in views])["pixel_values"]
+            buf = self.out[self.slot]
+            if buf is None or buf.shape[0] < len(imgs):
+                buf = torch.empty((len(imgs), 3, self.p.out_size, self.p.out_size), dtype=self.p.out_dtype,
+                                  device=self.p.device)
+                self.out[self.slot] = buf
+            out = self.p.preprocess([dev[o:o + h * w * 3].view(h, w, 3) for o, (h, w, _) in views],
+                                    out=buf[:len(imgs)])["pixel_values"]
             done = torch.cuda.Event()
             done.record()
         self.pending = (out, done)
@@ -153,5 +162,4 @@ class ImageBatchPipeline:
     def result(self) -> torch.Tensor:
         out, done = self.pending
         torch.cuda.current_stream().wait_event(done)
-        out.record_stream(torch.cuda.current_stream())
-        return out
+        return out          # valid until the same slot is submitted again (two batches later)
