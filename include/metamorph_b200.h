@@ -159,6 +159,12 @@ int mm_decode_state_step(int* in_image_mode, int* total_image_tokens, int* total
                          const int* argmax_tok, const int* forced, int forced_ld, int step, int B,
                          int num_image_tokens, int max_new_tokens, int max_ids, int start_id, int end_id, int eos0,
                          int eos1, const void* pred_z, void* img_out, int max_img, int C, cudaStream_t s);
+/* continuous batching: per-slot output limit; a negative forced entry = free running */
+int mm_decode_state_step_slots(int* in_image_mode, int* total_image_tokens, int* total_output, int* finished, int* pos,
+                               int* n_ids, int* n_img, int* ids_out, int* append_kind, int* next_token,
+                               const int* argmax_tok, const int* forced, int forced_ld, const int* max_new_slot, int B,
+                               int num_image_tokens, int max_ids, int start_id, int end_id, int eos0, int eos1,
+                               const void* pred_z, void* img_out, int max_img, int C, cudaStream_t s);
 int mm_decode_next_input(const int* kind, const int* tok, const void* embed, const void* pred, void* x, int B,
                          int H, cudaStream_t s);
 int mm_decode_select_hidden(const int* mode, const void* hidden, const void* pred, void* out, int B, int H,

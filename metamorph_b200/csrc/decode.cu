@@ -527,7 +527,7 @@ __global__ void decode_state_kernel(DecodeState st, const int* __restrict__ argm
                                     int num_image_tokens, int max_new_tokens, int max_ids,
                                     int start_id, int end_id, int eos0, int eos1,
                                     const bf16* __restrict__ pred_z, bf16* __restrict__ img_out,
-                                    int max_img, int C) {
+                                    int max_img, int C, const int* __restrict__ max_new_slot) {
   const int b = blockIdx.x;
   __shared__ int s_store_img;
   __shared__ int s_slot;
@@ -537,7 +537,11 @@ __global__ void decode_state_kernel(DecodeState st, const int* __restrict__ argm
     if (!st.finished[b]) {
       // forced schedule is indexed by this sequence's own step count (device-resident -> graph replayable)
       const int fidx = st.total_output[b] < forced_ld ? st.total_output[b] : forced_ld - 1;
-      const int tok = forced ? forced[(long long)b * forced_ld + fidx] : argmax_tok[b];
+      // a negative entry in the forced schedule means "free running" for that position (continuous batching mixes
+      // teacher-forced and free sequences in one batch)
+      const int ftok = forced ? forced[(long long)b * forced_ld + fidx] : -1;
+      const int tok = ftok >= 0 ? ftok : argmax_tok[b];
+      const int max_new = max_new_slot ? max_new_slot[b] : max_new_tokens;
       const int mode = st.in_image_mode[b];
       if (!mode && tok == start_id) {
         st.in_image_mode[b] = 1;
@@ -565,7 +569,7 @@ __global__ void decode_state_kernel(DecodeState st, const int* __restrict__ argm
       st.total_output[b]++;
       st.next_token[b] = tok;
       if (tok == eos0 || tok == eos1) st.finished[b] = 1;
-      else if (st.total_output[b] > max_new_tokens) st.finished[b] = 1;
+      else if (st.total_output[b] > max_new) st.finished[b] = 1;
       st.pos[b]++;
     }
     st.append_kind[b] = kind;
@@ -752,7 +756,26 @@ MM_API int mm_decode_state_step(int* in_image_mode, int* total_image_tokens, int
                  n_ids, n_img, ids_out, append_kind, next_token};
   decode_state_kernel<<<B, 128, 0, stream>>>(st, argmax_tok, forced, forced_ld, step, B, num_image_tokens,
                                              max_new_tokens, max_ids, start_id, end_id, eos0, eos1,
-                                             (const bf16*)pred_z, (bf16*)img_out, max_img, C);
+                                             (const bf16*)pred_z, (bf16*)img_out, max_img, C, nullptr);
+  MM_CHECK_LAUNCH();
+  return MM_OK;
+}
+
+// Same state machine with a per-slot output limit (max_new_slot[b], device) — continuous batching:
+// every slot of the batch serves a different request.
+MM_API int mm_decode_state_step_slots(int* in_image_mode, int* total_image_tokens, int* total_output,
+                                      int* finished, int* pos, int* n_ids, int* n_img, int* ids_out,
+                                      int* append_kind, int* next_token, const int* argmax_tok,
+                                      const int* forced, int forced_ld, const int* max_new_slot, int B,
+                                      int num_image_tokens, int max_ids, int start_id, int end_id, int eos0,
+                                      int eos1, const void* pred_z, void* img_out, int max_img, int C,
+                                      cudaStream_t stream) {
+  MM_CHECK_ARG(max_new_slot != nullptr, "mm_decode_state_step_slots: per-slot limits missing");
+  DecodeState st{in_image_mode, total_image_tokens, total_output, finished, pos,
+                 n_ids, n_img, ids_out, append_kind, next_token};
+  decode_state_kernel<<<B, 128, 0, stream>>>(st, argmax_tok, forced, forced_ld, 0, B, num_image_tokens, 0, max_ids,
+                                             start_id, end_id, eos0, eos1, (const bf16*)pred_z, (bf16*)img_out,
+                                             max_img, C, max_new_slot);
   MM_CHECK_LAUNCH();
   return MM_OK;
 }

@@ -446,6 +446,17 @@ def decode_state_step(st: dict, argmax_tok, forced, step, B, num_image_tokens, m
          c_int(img_out.shape[2]), stream_ptr())
 
 
+def decode_state_step_slots(st: dict, argmax_tok, forced, max_new_slot, B, num_image_tokens, start_id, end_id, eos0,
+                            eos1, pred_z, img_out):
+    """The greedy_decode state machine with one output limit per batch slot (continuous batching)."""
+    call("mm_decode_state_step_slots", ptr(st["in_image_mode"]), ptr(st["total_image_tokens"]),
+         ptr(st["total_output"]), ptr(st["finished"]), ptr(st["pos"]), ptr(st["n_ids"]), ptr(st["n_img"]),
+         ptr(st["ids_out"]), ptr(st["append_kind"]), ptr(st["next_token"]), ptr(argmax_tok), ptr(forced),
+         c_int(forced.stride(0) if forced is not None else 0), ptr(max_new_slot), c_int(B), c_int(num_image_tokens),
+         c_int(st["ids_out"].shape[1]), c_int(start_id), c_int(end_id), c_int(eos0), c_int(eos1), ptr(pred_z),
+         ptr(img_out), c_int(img_out.shape[1]), c_int(img_out.shape[2]), stream_ptr())
+
+
 def decode_next_input(kind, tok, embed_w, pred, x):
     call("mm_decode_next_input", ptr(kind), ptr(tok), ptr(embed_w), ptr(pred), ptr(x), c_int(x.shape[0]),
          c_int(x.shape[1]), stream_ptr())

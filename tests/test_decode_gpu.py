@@ -204,3 +204,51 @@ def test_engine_with_stack_kernel_matches_default_path(cuda_device):
         assert outs[True][1][b].shape == outs[False][1][b].shape
         if outs[True][1][b].shape[0]:
             _close(outs[True][1][b], outs[False][1][b], 3e-2, f"image embeds seq {b}")
+
+
+def test_continuous_batching_matches_single_request_decodes(cuda_device):
+    """requests streamed through 2 slots (queueing, slot reuse, admission between steps, per-slot output
+    limits, mixed teacher-forced / free-running sequences) must each reproduce their own stand-alone greedy_decode."""
+    from metamorph_b200.engine.serve import ContinuousBatcher
+    from oracle.weights import TINY, make_weights
+    from tests.helpers import build_product_model
+    model = build_product_model(TINY, make_weights(TINY), num_image_tokens=4)
+    model.eval()
+    g = torch.Generator().manual_seed(17)
+    specs = [(10, 14), (7, 9), (3, 20), (9, 6), (4, 12), (12, 5)]          # (prompt positions, max_new_tokens)
+    reqs = []
+    for i, (P, n_new) in enumerate(specs):
+        prompt = torch.randint(0, 128000, (1, P), generator=g)
+        forced = torch.randint(0, 128000, (n_new + 2,), generator=g).to(torch.int32)
+        if i == 0:
+            forced[2] = 128256; forced[9] = 128257
+        if i == 2:
+            forced[0] = 128256; forced[7] = 128256
+        if i == 3:
+            forced[3] = 128009                                              # EOS ends request 3 early
+        reqs.append((model.get_model().embed_tokens(prompt.cuda()), n_new, forced))
+    srv = ContinuousBatcher(model, max_slots=2, max_context=64, max_new_tokens=24, poll_every=3)
+    rids = [srv.submit(e, max_new_tokens=n, forced_tokens=f) for e, n, f in reqs]
+    free_rid = srv.submit(reqs[1][0], max_new_tokens=5)                     # a free-running request in the mix
+    results, streamed = {}, {}
+    for rid, kind, payload in srv.run():
+        if kind == "done":
+            results[rid] = payload
+        else:
+            streamed.setdefault((rid, kind), []).append(payload)
+    assert set(results) == set(rids) | {free_rid}
+    for rid, (emb, n_new, forced) in zip(rids, reqs):
+        ids1, img1 = model.greedy_decode(None, None, emb, max_new_tokens=n_new, output_image=True,
+                                         forced_tokens=forced.reshape(1, -1))
+        ids, img = results[rid]
+        assert ids.cpu().tolist() == ids1[0].cpu().tolist(), f"request {rid}: ids differ"
+        n1 = img1.shape[0] if img1.dim() == 2 else 0
+        assert img.shape[0] == n1, f"request {rid}: {img.shape[0]} vs {n1} visual embeddings"
+        if n1:
+            _close(img, img1, 3e-2, f"request {rid} image embeds")
+        # the streamed chunks are the same data, in order
+        cat = torch.cat(streamed.get((rid, "ids"), [torch.empty(0, dtype=torch.int32, device="cuda")]))
+        assert cat.cpu().tolist() == ids.cpu().tolist()
+    ids_f, img_f = results[free_rid]
+    assert 1 <= ids_f.numel() + img_f.shape[0] <= 6
+    assert results[rids[3]][0].cpu().tolist()[-1] == 128009 and results[rids[3]][0].numel() == 4
