@@ -236,7 +236,10 @@ class HotPath:
         seqlens = plan.seqlens.to(dev, non_blocking=True)
         if plan.padding_side != "right" and bool((plan.seqlens != T).any()):
             raise NotImplementedError("left padding with ragged lengths is not supported by the fused attention")
-        ctx = StackContext(B=B, T=T, pos=pos, seqlens=seqlens)
+        flat_segments = None
+        if plan.segments is not None:
+            flat_segments = [(r * T + off, n) for r, segs in enumerate(plan.segments) for off, n in segs]
+        ctx = StackContext(B=B, T=T, pos=pos, seqlens=seqlens, segments=flat_segments)
         stack = m.stack
         layers = [l.weights() for l in model.layers]
         hidden = stack.forward(layers, model.norm.weight.data, x, ctx, save=want_grad, n_save_gu=n_save_gu)

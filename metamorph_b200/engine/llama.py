@@ -102,6 +102,9 @@ class StackContext:
     pos: torch.Tensor            # int32 [B*T]
     seqlens: Optional[torch.Tensor]
     saved: List[LayerSaved] = field(default_factory=list)
+    # sequence packing: flat (first row, length) of every sample in the [B*T] token dimension; attention runs per
+    # segment (block-diagonal causal), every other kernel is per token and does not care
+    segments: Optional[List[tuple]] = None
     x_final_in: Optional[torch.Tensor] = None  # input of the final norm
 
 
@@ -130,8 +133,16 @@ class LlamaStack:
         del n1
         ops.rope_(qkv, ctx.pos, self.cos, self.sin, Hq + Hkv, dh)
         q, k, v = qkv[:, :Hq * dh], qkv[:, Hq * dh:(Hq + Hkv) * dh], qkv[:, (Hq + Hkv) * dh:]
-        attn, lse = ops.attn_fwd(q, k, v, B, T, Hq, Hkv, dh, True, self.scale, seqlens=ctx.seqlens,
-                                 need_lse=save)
+        if ctx.segments is None:
+            attn, lse = ops.attn_fwd(q, k, v, B, T, Hq, Hkv, dh, True, self.scale, seqlens=ctx.seqlens,
+                                     need_lse=save)
+        else:
+            attn = torch.zeros((x.shape[0], Hq * dh), dtype=torch.bfloat16, device=x.device)   # pad rows stay finite
+            lse = []
+            for r0, n in ctx.segments:
+                _, l = ops.attn_fwd(q[r0:r0 + n], k[r0:r0 + n], v[r0:r0 + n], 1, n, Hq, Hkv, dh, True, self.scale,
+                                    out=attn[r0:r0 + n], need_lse=save)
+                lse.append(l)
         h_mid = ops.gemm(attn, w.wo, resid=x, epilogue=ops.EPI_RESID)
         n2 = ops.rmsnorm(h_mid, w.ln2, d.rms_eps)
         gu = torch.empty((x.shape[0], 2 * d.intermediate), dtype=torch.bfloat16, device=x.device) \
@@ -188,12 +199,20 @@ class LlamaStack:
         # ---- attention: h_mid = x + o_proj(attn(rope(qkv(norm1(x)))))
         ops.gemm(dh_mid, s.attn, a_mn=True, b_mn=True, out=g.wo, accumulate=accumulate)  # dWo
         dattn = ops.gemm(dh_mid, w.wo, b_mn=True)                                         # [M, Hq*dh]
-        dqkv = torch.empty_like(s.qkv)
         q, k, v = s.qkv[:, :Hq * dh], s.qkv[:, Hq * dh:(Hq + Hkv) * dh], s.qkv[:, (Hq + Hkv) * dh:]
-        self._attn_ws = ops.attn_bwd(q, k, v, s.attn, dattn, s.lse, dqkv[:, :Hq * dh],
-                                     dqkv[:, Hq * dh:(Hq + Hkv) * dh], dqkv[:, (Hq + Hkv) * dh:],
-                                     B, T, Hq, Hkv, dh, self.scale, seqlens=ctx.seqlens,
-                                     workspace=self._attn_ws)
+        if ctx.segments is None:
+            dqkv = torch.empty_like(s.qkv)
+            self._attn_ws = ops.attn_bwd(q, k, v, s.attn, dattn, s.lse, dqkv[:, :Hq * dh],
+                                         dqkv[:, Hq * dh:(Hq + Hkv) * dh], dqkv[:, (Hq + Hkv) * dh:],
+                                         B, T, Hq, Hkv, dh, self.scale, seqlens=ctx.seqlens,
+                                         workspace=self._attn_ws)
+        else:
+            dqkv = torch.zeros_like(s.qkv)
+            dq, dk, dv = dqkv[:, :Hq * dh], dqkv[:, Hq * dh:(Hq + Hkv) * dh], dqkv[:, (Hq + Hkv) * dh:]
+            for (r0, n), lse in zip(ctx.segments, s.lse):
+                self._attn_ws = ops.attn_bwd(q[r0:r0 + n], k[r0:r0 + n], v[r0:r0 + n], s.attn[r0:r0 + n],
+                                             dattn[r0:r0 + n], lse, dq[r0:r0 + n], dk[r0:r0 + n], dv[r0:r0 + n],
+                                             1, n, Hq, Hkv, dh, self.scale, workspace=self._attn_ws)
         del dattn
         ops.rope_(dqkv, ctx.pos, self.cos, self.sin, Hq + Hkv, dh, backward=True)
         n1 = ops.rmsnorm(s.x_in, w.ln1, d.rms_eps)

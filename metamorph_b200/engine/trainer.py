@@ -103,13 +103,16 @@ class FusedGradProvider(GradProvider):
 class TrainEngine:
     def __init__(self, model, lr: float = 6.93e-5, betas=(0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 0.0, max_grad_norm: Optional[float] = None, total_steps: int = 1000,
-                 warmup_ratio: float = 0.03, constant_lr: bool = False, n_save_gu_layers: int = 0):
+                 warmup_ratio: float = 0.03, constant_lr: bool = False, n_save_gu_layers: int = 0,
+                 pack_sequences: bool = False, pack_len: Optional[int] = None):
         self.model = model
         self.hot = HotPath(model)
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
         self.max_grad_norm = max_grad_norm
         self.total_steps, self.warmup_ratio, self.constant_lr = total_steps, warmup_ratio, constant_lr
         self.n_save_gu_layers = n_save_gu_layers
+        # lay the samples of a batch end to end (block-diagonal attention) instead of padding them
+        self.pack_sequences, self.pack_len = pack_sequences, pack_len
         self.step_count = 0
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank() if self.world > 1 else 0
@@ -170,6 +173,11 @@ class TrainEngine:
         if images.dtype != torch.bfloat16:
             images = images.to(torch.bfloat16)
         plan = m.plan_inputs(batch["input_ids"], batch.get("attention_mask"), batch["labels"], images.shape[0])
+        if self.pack_sequences:
+            from ..model.interleave_plan import pack_plan
+            padded_positions = plan.batch * plan.seq_len
+            plan = pack_plan(plan, self.pack_len)
+            self.last_padding_saved = padded_positions - plan.batch * plan.seq_len
         res, _ = self.hot.forward_backward(plan, images, self.provider, want_grad=True,
                                            n_save_gu=self.n_save_gu_layers,
                                            train_embed=("model.embed_tokens.weight" in self.opt),

@@ -35,6 +35,9 @@ class InterleavePlan:
     target_image_idx: List[int]    # images (flat index) whose tower features are regression targets
     image_placeholder: List[int]   # complement bookkeeping of the reference (:268, :415-423)
     padding_side: str
+    # sequence packing: per packed row, the (start, length) of every sample placed in it; None = one
+    # sample per row. Attention is block-diagonal over these segments; everything else is per token.
+    segments: Optional[List[List[tuple]]] = None
 
     @property
     def batch(self) -> int:
@@ -145,3 +148,58 @@ def build_interleave_plan(input_ids, attention_mask, labels, num_images: int, im
                           torch.from_numpy(new_impos), torch.from_numpy(new_mask),
                           torch.from_numpy(pos_ids), torch.from_numpy(seqlens), targets,
                           placeholder, padding_side)
+
+
+def pack_plan(plan: InterleavePlan, pack_len: Optional[int] = None) -> InterleavePlan:
+    """Sequence packing: the samples of a right-padded plan are laid end to end into rows of
+    `pack_len` positions (next-fit in the original sample order, so the row-major order of the answer-image rows still
+    matches the order of the regression targets, metamorph_arch.py:415-423). The reference pads every sample to the
+    batch maximum (metamorph_arch.py:361-399); packing feeds the same tokens, labels and position ids through
+    block-diagonal causal attention, so the losses and gradients are those of the padded batch while the padding rows
+    (and their FLOPs) disappear. The label at each segment start is forced to IGNORE_INDEX: in the padded layout that
+    label is dropped by the shift (metamorph_llama.py:404-405), here it would become the target of the previous
+    sample's last token."""
+    if plan.padding_side != "right":
+        raise NotImplementedError("packing expects a right-padded plan")
+    B, T = plan.batch, plan.seq_len
+    Tp = int(pack_len or T)
+    lens = [int(x) for x in plan.seqlens.tolist()]
+    if max(lens) > Tp:
+        raise ValueError(f"a sample of {max(lens)} positions does not fit pack_len {Tp}")
+    rows: List[List[int]] = [[]]
+    used = 0
+    for b, n in enumerate(lens):
+        if n == 0:
+            continue
+        if used + n > Tp and rows[-1]:
+            rows.append([])
+            used = 0
+        rows[-1].append(b)
+        used += n
+    R = len(rows)
+    row_map = np.full((R, Tp), ROW_PAD, dtype=np.int32)
+    labels = np.full((R, Tp), IGNORE_INDEX, dtype=np.int64)
+    ipos = np.zeros((R, Tp), dtype=np.int64)
+    mask = np.zeros((R, Tp), dtype=bool)
+    pos = np.zeros((R, Tp), dtype=np.int64)
+    seqlens = np.zeros((R,), dtype=np.int32)
+    segments: List[List[tuple]] = []
+    src = dict(row_map=plan.row_map.numpy(), labels=plan.labels.numpy(), ipos=plan.image_positions.numpy(),
+               pos=plan.position_ids.numpy())
+    for r, members in enumerate(rows):
+        off, segs = 0, []
+        for b in members:
+            n = lens[b]
+            row_map[r, off:off + n] = src["row_map"][b, :n]
+            labels[r, off:off + n] = src["labels"][b, :n]
+            labels[r, off] = IGNORE_INDEX
+            ipos[r, off:off + n] = src["ipos"][b, :n]
+            pos[r, off:off + n] = src["pos"][b, :n]
+            mask[r, off:off + n] = True
+            segs.append((off, n))
+            off += n
+        seqlens[r] = off
+        segments.append(segs)
+    return InterleavePlan(torch.from_numpy(row_map), torch.from_numpy(labels), torch.from_numpy(ipos),
+                          torch.from_numpy(mask), torch.from_numpy(pos), torch.from_numpy(seqlens),
+                          list(plan.target_image_idx), list(plan.image_placeholder), "right", segments)
