@@ -15,6 +15,7 @@ import torch
 
 from .. import ops
 from ..constants import EOS_TOKEN_IDS, IMAGE_END_TOKEN_ID, IMAGE_START_TOKEN_ID
+from .decode_step import decode_heads, decoder_stack_step
 from .llama import StackContext
 
 
@@ -85,18 +86,7 @@ class DecodeEngine:
         logits = torch.empty((B, (V + 7) // 8 * 8), dtype=torch.float32, device=dev)
 
         def heads_and_state(h_pre_norm, step):
-            hidden = ops.rmsnorm(h_pre_norm, model.norm.weight.data, d.rms_eps)
-            # image-mode branch computed for every sequence, selected per sequence (graph friendly)
-            vh, pj = m.vision_head, model.mm_projector
-            z = ops.skinny_gemm(hidden, vh.fc1.weight.data, bias=vh.fc1.bias.data, epilogue=ops.SK_BIAS_GELU)
-            z = ops.skinny_gemm(z, vh.fc2.weight.data, bias=vh.fc2.bias.data, epilogue=ops.SK_BIAS)
-            pred_z = ops.l2norm_rows(z) if m.normalize_vision else z
-            p1 = ops.skinny_gemm(pred_z, pj.fc1.weight.data, bias=pj.fc1.bias.data, epilogue=ops.SK_BIAS_GELU)
-            prediction = ops.skinny_gemm(p1, pj.fc2.weight.data, bias=pj.fc2.bias.data, epilogue=ops.SK_BIAS)
-            h_eff = torch.empty_like(hidden)
-            ops.decode_select_hidden(st["in_image_mode"], hidden, prediction, h_eff)
-            ops.skinny_gemm(h_eff, m.lm_head.weight.data, out=logits[:, :V])
-            tok = ops.argmax_rows(logits, V)
+            tok, pred_z, prediction = decode_heads(m, h_pre_norm, st["in_image_mode"], logits, V)
             ops.decode_state_step(st, tok, forced, step, B, ntok, max_new_tokens, start_image_token_id,
                                   end_image_token_id, eos0, eos1, pred_z, img_out)
             ops.decode_next_input(st["append_kind"], st["next_token"], model.embed_tokens.weight.data,
@@ -115,18 +105,9 @@ class DecodeEngine:
         def one_step_body():
             # position of the token being fed = pos - 1 (the state step already advanced pos)
             cur_pos = st["pos"] - 1
-            x = xin
             if stack_plan is not None:
-                return ops.decode_stack(stack_plan, x, kc, vc, cur_pos, stack.cos, stack.sin, stack.scale, d.rms_eps)
-            for i, w in enumerate(layers):
-                n1 = ops.rmsnorm(x, w.ln1, d.rms_eps)
-                qkv = ops.skinny_gemm(n1, w.wqkv)
-                attn = ops.decode_attn(qkv, kc[i], vc[i], cur_pos, stack.cos, stack.sin, Hq, Hkv, dh, stack.scale)
-                hmid = ops.skinny_gemm(attn, w.wo, resid=x, epilogue=ops.SK_RESID)
-                n2 = ops.rmsnorm(hmid, w.ln2, d.rms_eps)
-                act = ops.skinny_gemm(n2, w.wgu, epilogue=ops.SK_SWIGLU)
-                x = ops.skinny_gemm(act, w.wd, resid=hmid, epilogue=ops.SK_RESID)
-            return x
+                return ops.decode_stack(stack_plan, xin, kc, vc, cur_pos, stack.cos, stack.sin, stack.scale, d.rms_eps)
+            return decoder_stack_step(layers, xin, kc, vc, cur_pos, stack)
 
         # One captured CUDA graph is replayed for every step (launch-bound inner loop): all per-step state,
         # including the index into the forced-token schedule, lives in device memory.

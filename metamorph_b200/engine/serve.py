@@ -10,7 +10,7 @@ embeddings). Here up to `max_slots` (<= 8) requests share every weight-streaming
   * the step itself (decoder stack + heads + argmax + state machine + next-input gather) is ONE captured CUDA graph
     replayed for all slots, exactly the kernels of DecodeEngine; idle / finished slots are frozen by the device state;
   * the host polls the tiny state arrays every `poll_every` steps, hands out finished requests, streams the new text
-    ids / visual embeddings of running ones (`events()`), and refills the freed slots.
+    ids / visual embeddings of running ones (`run()` yields them), and refills the freed slots.
 Every request's output equals what `greedy_decode` produces for it alone (tests/test_decode_gpu.py).
 """
 from __future__ import annotations
@@ -23,6 +23,7 @@ import torch
 
 from .. import ops
 from ..constants import EOS_TOKEN_IDS, IMAGE_END_TOKEN_ID, IMAGE_START_TOKEN_ID
+from .decode_step import decode_heads, decoder_stack_step
 from .llama import StackContext
 
 
@@ -88,30 +89,9 @@ class ContinuousBatcher:
 
     # ------------------------------------------------------------------ one device step for all slots
     def _step_body(self):
-        m, d, st = self.m, self.d, self.st
-        Hq, Hkv, dh = d.n_heads, d.n_kv_heads, d.head_dim
-        cur_pos = st["pos"] - 1
-        x = self.xin
-        for i, w in enumerate(self.layers):
-            n1 = ops.rmsnorm(x, w.ln1, d.rms_eps)
-            qkv = ops.skinny_gemm(n1, w.wqkv)
-            attn = ops.decode_attn(qkv, self.kc[i], self.vc[i], cur_pos, self.stack.cos, self.stack.sin, Hq, Hkv, dh,
-                                   self.stack.scale)
-            hmid = ops.skinny_gemm(attn, w.wo, resid=x, epilogue=ops.SK_RESID)
-            n2 = ops.rmsnorm(hmid, w.ln2, d.rms_eps)
-            act = ops.skinny_gemm(n2, w.wgu, epilogue=ops.SK_SWIGLU)
-            x = ops.skinny_gemm(act, w.wd, resid=hmid, epilogue=ops.SK_RESID)
-        hidden = ops.rmsnorm(x, self.inner.norm.weight.data, d.rms_eps)
-        vh, pj = m.vision_head, self.inner.mm_projector
-        z = ops.skinny_gemm(hidden, vh.fc1.weight.data, bias=vh.fc1.bias.data, epilogue=ops.SK_BIAS_GELU)
-        z = ops.skinny_gemm(z, vh.fc2.weight.data, bias=vh.fc2.bias.data, epilogue=ops.SK_BIAS)
-        pred_z = ops.l2norm_rows(z) if m.normalize_vision else z
-        p1 = ops.skinny_gemm(pred_z, pj.fc1.weight.data, bias=pj.fc1.bias.data, epilogue=ops.SK_BIAS_GELU)
-        prediction = ops.skinny_gemm(p1, pj.fc2.weight.data, bias=pj.fc2.bias.data, epilogue=ops.SK_BIAS)
-        h_eff = torch.empty_like(hidden)
-        ops.decode_select_hidden(st["in_image_mode"], hidden, prediction, h_eff)
-        ops.skinny_gemm(h_eff, m.lm_head.weight.data, out=self.logits[:, :self.V])
-        tok = ops.argmax_rows(self.logits, self.V)
+        st = self.st
+        x = decoder_stack_step(self.layers, self.xin, self.kc, self.vc, st["pos"] - 1, self.stack)
+        tok, pred_z, prediction = decode_heads(self.m, x, st["in_image_mode"], self.logits, self.V)
         ops.decode_state_step_slots(st, tok, self.forced, self.max_new_slot, self.B, self.ntok, self.start_id,
                                     self.end_id, self.eos0, self.eos1, pred_z, self.img_out)
         ops.decode_next_input(st["append_kind"], st["next_token"], self.inner.embed_tokens.weight.data, prediction,
