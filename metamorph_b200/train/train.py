@@ -70,6 +70,8 @@ class TrainingArguments:
     gradient_checkpointing: bool = field(default=True)  # accepted for CLI compatibility; selective recompute is built in
     save_gu_layers: int = field(default=32)
     save_steps: int = field(default=0)          # > 0: write output_dir/checkpoint-<step> every save_steps steps
+    pack_sequences: bool = field(default=False)  # lay a batch's samples end to end instead of padding
+    pack_len: Optional[int] = field(default=None)  # row length of the packed layout (default: the batch maximum)
 
 
 def rank0_print(*args):
@@ -140,7 +142,8 @@ def train(attn_implementation=None, data_module_factory: Optional[Callable[..., 
 
     engine = TrainEngine(model, lr=training_args.learning_rate, weight_decay=training_args.weight_decay,
                          max_grad_norm=training_args.max_grad_norm, total_steps=training_args.max_steps,
-                         warmup_ratio=training_args.warmup_ratio, n_save_gu_layers=training_args.save_gu_layers)
+                         warmup_ratio=training_args.warmup_ratio, n_save_gu_layers=training_args.save_gu_layers,
+                         pack_sequences=training_args.pack_sequences, pack_len=training_args.pack_len)
     if data_module_factory is not None:
         batches = iter(data_module_factory(None, data_args))
     elif data_args.data_path.startswith("synthetic"):
