@@ -158,7 +158,9 @@ class TrainEngine:
     def current_lr(self) -> float:
         if self.constant_lr:
             return self.lr
-        return cosine_lr(self.step_count, self.total_steps, self.lr, self.warmup_ratio)
+        # HF Trainer steps the scheduler AFTER the optimizer: optimizer step k (1-based) runs with lambda(k - 1), so the
+        # very first update has lr 0 (LambdaLR starts at lambda(0)); step_count is already k inside step()
+        return cosine_lr(max(self.step_count - 1, 0), self.total_steps, self.lr, self.warmup_ratio)
 
     # -------------------------------------------------------------- one train step
     def step(self, batch: dict) -> dict:

@@ -110,7 +110,7 @@ def test_training_checkpoint_resume(cuda_device, tmp_path):
         p32, m, v, p16 = saved[n]
         assert torch.equal(st.p32, p32) and torch.equal(st.m, m) and torch.equal(st.v, v) and torch.equal(st.p16, p16), n
     from metamorph_b200.engine.trainer import cosine_lr
-    assert e_b.current_lr == cosine_lr(2, 10, 1e-3, 0.2)                # schedule position follows the step counter
+    assert e_b.current_lr == cosine_lr(1, 10, 1e-3, 0.2)                # lr of (restored) step 2 = lambda(1), as HF
     losses_b = [float(e_b.step(_batch())["loss"]) for _ in range(2)]
     for la, lb in zip(losses_a, losses_b):
         assert abs(la - lb) <= 2e-3 * abs(la) + 1e-3, (losses_a, losses_b)
