@@ -113,3 +113,24 @@ def test_latest_checkpoint_discovery(tmp_path):
             (d / ck.TRAINER_STATE_NAME).write_text("{}")
     (tmp_path / "checkpoint-final").mkdir()
     assert ck.latest_checkpoint(str(tmp_path)) == str(tmp_path / "checkpoint-20")   # 100 is incomplete (no state file)
+
+
+def test_hf_loader_reads_our_shards(tiny_model, tmp_path):
+    """HF's own `from_pretrained` (index parsing, shard loading, safetensors metadata) must accept the files: load the
+    LLaMA part of the checkpoint into a stock `LlamaForCausalLM` and compare every tensor."""
+    from transformers import LlamaConfig, LlamaForCausalLM
+    from oracle.weights import TINY
+    ck.save_model(tiny_model, str(tmp_path), max_shard_size="40MB")
+    cfg = LlamaConfig(hidden_size=TINY["hidden"], intermediate_size=TINY["inter"], num_hidden_layers=TINY["layers"],
+                      num_attention_heads=TINY["heads"], num_key_value_heads=TINY["kv_heads"], head_dim=TINY["head_dim"],
+                      vocab_size=TINY["vocab"], rms_norm_eps=TINY["rms_eps"], tie_word_embeddings=False,
+                      attention_bias=False)
+    hf = LlamaForCausalLM.from_pretrained(str(tmp_path), config=cfg, torch_dtype=torch.bfloat16)
+    ours = tiny_model.state_dict()
+    n = 0
+    for k, v in hf.state_dict().items():
+        if "rotary" in k:
+            continue
+        assert torch.equal(v.cpu(), ours[k].cpu()), k
+        n += 1
+    assert n == 3 + 9 * TINY["layers"]          # embed, norm, lm_head + 9 tensors per decoder layer
