@@ -1,5 +1,6 @@
-"""`load_pretrained_model` (metamorph/model/builder.py:13-144), full-model branch (:86-92, :120-142).
-LoRA / 4-bit / 8-bit / projector-only branches are unused by the reference scripts: out of scope."""
+"""`load_pretrained_model` (metamorph/model/builder.py:13-144): the full-model branch (:86-92, :120-142) and the
+projector-only branch (:73-84: base LLaMA weights + the stage-1 `mm_projector.bin` of `model_path`).
+LoRA / 4-bit / 8-bit branches are unused by the reference scripts: out of scope."""
 from __future__ import annotations
 
 import torch
@@ -13,15 +14,32 @@ def load_pretrained_model(model_path, model_base, model_name, load_8bit=False, l
                           **kwargs):
     if load_8bit or load_4bit:
         raise NotImplementedError("quantised loading is out of scope for the B200 hot path")
-    if "lora" in model_name.lower() or model_base is not None:
-        raise NotImplementedError("LoRA / projector-only checkpoints are out of scope (unused by the scripts)")
+    if "lora" in model_name.lower():
+        raise NotImplementedError("LoRA checkpoints are out of scope (unused by the scripts)")
     if torch_dtype != torch.bfloat16:
         # the kernels compute in bf16 (fp32 accumulate); fp16 checkpoints are converted on load
         torch_dtype = torch.bfloat16
     from transformers import AutoTokenizer
-    tokenizer = AutoTokenizer.from_pretrained(model_path, use_fast=False)
-    model = MetaMorphLlamaForCausalLM.from_pretrained(model_path, torch_dtype=torch_dtype, device=device,
-                                                      vision_delay_load=False, **kwargs)
+    if model_base is not None:
+        # "this may be mm projector only" (builder.py:73-84): language model from model_base, config and the stage-1
+        # projector weights from model_path
+        import json
+        import os
+        from .. import checkpoint
+        from .metamorph_llama import MetaMorphConfig
+        tokenizer = AutoTokenizer.from_pretrained(model_base, use_fast=False)
+        with open(os.path.join(model_path, "config.json")) as fh:
+            raw = json.load(fh)
+        raw.pop("model_type", None)
+        raw.pop("architectures", None)
+        model = MetaMorphLlamaForCausalLM.from_pretrained(model_base, torch_dtype=torch_dtype, device=device,
+                                                          config=MetaMorphConfig(**raw), vision_delay_load=False,
+                                                          **kwargs)
+        checkpoint.load_mm_projector(model, model_path)
+    else:
+        tokenizer = AutoTokenizer.from_pretrained(model_path, use_fast=False)
+        model = MetaMorphLlamaForCausalLM.from_pretrained(model_path, torch_dtype=torch_dtype, device=device,
+                                                          vision_delay_load=False, **kwargs)
     mm_use_im_start_end = getattr(model.config, "mm_use_im_start_end", False)
     mm_use_im_patch_token = getattr(model.config, "mm_use_im_patch_token", True)
     if mm_use_im_patch_token:
