@@ -2,7 +2,7 @@
 """Benchmark of the MetaMorph hot path (contract: task statement + BASELINE.json).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (default N=1)
-    python bench.py --impl reference --gpus N ...             # the reference's CPU algorithm (oracle port)
+    python bench.py --impl reference --gpus N ...             # the reference's own code on the host cores (oracle/_ref)
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 Workload (config.workload): BASELINE.json configs[1] at N=1 — LLaMA-3-8B + SigLIP-SO400M-14@384, bf16
@@ -104,44 +104,50 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU baseline: the oracle port (reference algorithm restated, oracle/restatement.py) on host cores
+# CPU baseline = THE REFERENCE'S OWN CODE on the host cores (oracle/ref_bench.py runs the copy that oracle/build_ref.py
+# vendors into oracle/_ref; it is a separate process so that `metamorph` resolves to the reference, not to this
+# repository's alias package). Falls back to the oracle port (oracle/restatement.py) only if that copy is missing.
 # ------------------------------------------------------------------------------------------------
-_CPU_THREADS = None
+def _run_ref_bench(argv, timeout):
+    cmd = [sys.executable, os.path.join(ROOT, "oracle", "ref_bench.py")] + argv
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    try:
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+    except subprocess.TimeoutExpired:
+        return None, "oracle/ref_bench.py timed out"
+    rows = []
+    for line in res.stdout.splitlines():
+        line = line.strip()
+        if line.startswith("{"):
+            try:
+                rows.append(json.loads(line))
+            except ValueError:
+                pass
+    summ = next((r for r in reversed(rows) if "summary" in r), None)
+    if summ is None or "error" in summ:
+        return None, (summ or {}).get("error") or (res.stderr.strip().splitlines() or ["no output"])[-1][:300]
+    return summ, None
 
 
-def best_cpu_threads():
-    """All host threads the reference can USE: on many-core boxes torch's fp32 GEMMs get slower past some thread
-    count (oversubscription, NUMA), so a 1-second calibration picks the fastest of {all, 96, 64, 48, 32, 16} threads
-    on an MLP-sized matmul; the choice is reported as `cores`."""
-    global _CPU_THREADS
-    if _CPU_THREADS is not None:
-        return _CPU_THREADS
-    import torch
-    n = os.cpu_count() or 1
-    cands = sorted({c for c in (n, 96, 64, 48, 32, 16) if 1 <= c <= n}, reverse=True)
-    a, b = torch.randn(1024, 4096), torch.randn(4096, 14336)
-    best, best_t = n, float("inf")
-    for c in cands:
-        torch.set_num_threads(c)
-        torch.mm(a, b)                                   # warm the pool at this size
-        t0 = time.perf_counter()
-        torch.mm(a, b)
-        torch.mm(a, b)
-        dt = time.perf_counter() - t0
-        if dt < best_t * 0.97:                           # prefer more threads on ties
-            best, best_t = c, dt
-    torch.set_num_threads(best)
-    _CPU_THREADS = best
-    return best
+def _train_sample_desc(summ, secs):
+    return (f"the reference's own MetaMorphLlamaForCausalLM.forward + loss.backward() ({summ['root']}; torch {summ['torch']} CPU, "
+            f"{summ['dtype']}, {summ['attention']} attention): full width, depth-reduced to {summ['layers']} LLaMA layer(s) + lm_head over all "
+            f"rows + both losses + {summ['siglip_layers']} SigLIP layers on {summ['images']} images, B=1, T={summ['seq_len']}; "
+            f"{secs:.2f} s per sample on {summ['threads']} of {summ['host_threads']} host threads (fastest of a 1-second "
+            f"thread-count calibration); tokens/s = (algorithmic FLOPs of the sample / seconds) / (algorithmic FLOPs per "
+            f"token of the 32-layer + 27-layer step), i.e. a LABELLED EXTRAPOLATION by FLOP ratio")
 
 
-def cpu_reference_sample(T=1024, layers=1, threads=None):
-    """One bounded sample: `layers` full-width LLaMA-3-8B decoder layers forward+backward on B=1, T tokens
-    (fp32 torch on all host threads). Returns (seconds, tokens/s extrapolated to the full 32-layer model
-    + lm_head at the same T by FLOP ratio)."""
+def reference_train_tokens_per_s(summ, secs, T):
+    return (summ["sample_flops"] / secs) / (train_flops_per_step(1, T, 4) / T)
+
+
+def cpu_port_sample(T=1024, layers=1):
+    """Fallback only (no oracle/_ref on this box): one full-width decoder layer of the oracle PORT, fwd+bwd, fp32."""
     import torch
     from oracle import restatement as R
-    torch.set_num_threads(threads if threads else best_cpu_threads())
     H, I, Hq, Hkv, dh = 4096, 14336, 32, 8, 128
     g = torch.Generator().manual_seed(0)
     p = {}
@@ -161,9 +167,45 @@ def cpu_reference_sample(T=1024, layers=1, threads=None):
     out.square().mean().backward()
     dt = time.time() - t0
     flops_sample = T * (6 * layers * (H * (2 * Hq * dh + 2 * Hkv * dh) + 3 * H * I) + 6 * layers * H * T)
-    flops_full_per_token = train_flops_per_step(1, T, 0) / T
-    tok_s = (flops_sample / dt) / flops_full_per_token
-    return dt, tok_s
+    return dt, (flops_sample / dt) / (train_flops_per_step(1, T, 0) / T)
+
+
+def cpu_train_baseline(T):
+    """cpu_baseline of the default run: one bounded sample of the reference's own train step per dtype (fp32 and bf16)."""
+    summ, err = _run_ref_bench(["train", "--steps", "1", "--warmup", "0", "--seq-len", str(T), "--dtype", "auto",
+                                "--budget-s", "1e9"], timeout=900)
+    if summ is None:
+        dt, tok_s = cpu_port_sample()
+        return {"value": tok_s, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                "sample": f"oracle/_ref unavailable ({err}); oracle port: 1 full-width layer fwd+bwd, B=1, T=1024, {dt:.1f} s, "
+                          "extrapolated by FLOP ratio"}
+    secs = summ["seconds"][0]
+    out = {"value": reference_train_tokens_per_s(summ, secs, T), "unit": UNIT, "cores": summ["threads"], "kind": "reference",
+           "sample": _train_sample_desc(summ, secs), "dtype": summ["dtype"], "measured_seconds": secs,
+           "probe_seconds_by_dtype": summ["probe_seconds"], "depth": {"llama_layers": summ["layers"], "siglip_layers": summ["siglip_layers"]}}
+    for name, t in summ["probe_seconds"].items():
+        out[f"value_{name}_first_sample"] = reference_train_tokens_per_s(summ, t, T)
+    return out
+
+
+def cpu_decode_baseline():
+    """Reference `generate()` -> `greedy_decode` WITHOUT a KV cache (metamorph_llama.py:502-597), batch 1, P=128, 32 new
+    tokens, full width, 2 decoder layers; extrapolated to 32 layers by the ratio of executed FLOPs."""
+    summ, err = _run_ref_bench(["decode", "--new-tokens", "32", "--prompt-len", "128", "--layers", "2", "--dtype", "f32"],
+                               timeout=900)
+    if summ is None:
+        return {"error": err, "kind": "reference"}
+    H, I, V = 4096, 14336, 128258
+    per_layer = H * (32 * 128 + 2 * 8 * 128 + 32 * 128) + 3 * H * I
+    P, n = summ["prompt_len"], summ["new_tokens"]
+    full = sum(2 * (32 * per_layer + H * V) * (P + t) + 4 * 32 * H * (P + t) ** 2 // 2 for t in range(n))
+    secs_full = summ["seconds"] * full / summ["executed_flops"]
+    return {"value": n / secs_full, "unit": "tokens/s", "cores": summ["threads"], "kind": "reference",
+            "measured_seconds": summ["seconds"], "new_tokens": n,
+            "sample": f"the reference's own generate() -> greedy_decode, no KV cache ({summ['root']}), batch 1, prompt {P}, {n} new text "
+                      f"tokens, full width, {summ['layers']} of 32 decoder layers, {summ['dtype']}: {summ['seconds']:.2f} s on "
+                      f"{summ['threads']} of {summ['host_threads']} host threads; extrapolated to 32 layers by executed-FLOP ratio "
+                      f"({full / summ['executed_flops']:.2f}x). The reference decodes one sequence at a time."}
 
 
 def decode_bench(model, dev, peaks, batch=8, prompt_len=128, new_positions=512):
@@ -200,7 +242,7 @@ def decode_bench(model, dev, peaks, batch=8, prompt_len=128, new_positions=512):
     steps = new_positions
     P = 7504666624
     kv_bytes = sum(2 * 8 * 128 * 2 * 32 * (prompt_len + t) for t in range(steps)) * batch
-    bytes_total = steps * (P * 2 + 2 * (4096 * 4096 + 4096 * 1152 + 1152 * 4096 + 4096 * 4096) * 2) + kv_bytes
+    bytes_total = steps * (P * 2 + (4096 * 4096 + 4096 * 1152 + 1152 * 4096 + 4096 * 4096) * 2) + kv_bytes
     hbm = peaks.get("hbm_gbs", 6650.0)
     achieved = bytes_total / (ms / 1e3) / 1e9
     model.train()
@@ -271,28 +313,40 @@ def preprocess_bench(dev, peaks, n_images=16, h=480, w=640, iters=20):
 
 
 def run_reference_impl(args):
-    """`--impl reference`: the reference's CPU algorithm (oracle port) on the host cores, same metric/config."""
-    import torch
+    """`--impl reference`: the reference's own CPU implementation of the path on the host cores, same metric/config.
+    Every step is one bounded sample (see oracle/ref_bench.py); rank 0 alone runs it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    threads = best_cpu_threads()
-    vals, secs = [], []
-    for i in range(args.warmup + args.steps):
-        dt, tok_s = cpu_reference_sample(T=1024, layers=1, threads=threads)
-        if i >= args.warmup:
-            vals.append(tok_s)
-            secs.append(dt)
-    v = sum(vals) / len(vals)
-    sample = ("oracle port (oracle/restatement.py, torch fp32): 1 full-width LLaMA-3-8B decoder layer fwd+bwd, "
-              "B=1, T=1024 per step; tokens/s extrapolated by algorithmic-FLOP ratio to 32 layers + lm_head")
+    T = args.seq_len
+    summ, err = _run_ref_bench(["train", "--steps", str(args.steps), "--warmup", str(args.warmup), "--seq-len", str(T),
+                                "--dtype", "auto", "--budget-s", "240"], timeout=1500)
+    if summ is not None:
+        secs = sum(summ["seconds"]) / len(summ["seconds"])
+        v = reference_train_tokens_per_s(summ, secs, T)
+        cpu = {"value": v, "unit": UNIT, "cores": summ["threads"], "kind": "reference", "sample": _train_sample_desc(summ, secs),
+               "dtype": summ["dtype"], "probe_seconds_by_dtype": summ["probe_seconds"]}
+        dtype = summ["dtype"]
+    else:
+        vals, ts = [], []
+        for i in range(args.warmup + args.steps):
+            dt, tok_s = cpu_port_sample()
+            if i >= args.warmup:
+                vals.append(tok_s)
+                ts.append(dt)
+        v, secs, dtype = sum(vals) / len(vals), sum(ts) / len(ts), "f32"
+        cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+               "sample": f"oracle/_ref unavailable ({err}); oracle port (oracle/restatement.py, torch fp32): 1 full-width decoder "
+                         "layer fwd+bwd, B=1, T=1024 per step; extrapolated by algorithmic-FLOP ratio"}
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype,
             "data": "synthetic",
-            "config": {"workload": "LLaMA-3-8B + SigLIP-SO400M bf16 instruction-tune step, seq 4096, batch 4/GPU "
-                                   "(reference arm: bounded CPU sample, see cpu_baseline.sample)"},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "config": {"workload": f"LLaMA-3-8B + SigLIP-SO400M instruction-tune step, seq {T}, batch {args.batch}/GPU "
+                                   "(reference arm: each step = one bounded full-width, depth-reduced CPU sample of the reference's "
+                                   "own forward+backward at the same T; value extrapolated by FLOP ratio, see cpu_baseline.sample)",
+                       "seq_len": T},
+            "cpu_baseline": cpu,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -433,19 +487,17 @@ def main():
                "api": "metamorph_b200.engine.trainer.TrainEngine.step(host batch: pinned images + int tensors)"}
 
     cpu = None
+    cpu_decode = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = best_cpu_threads()
-        cpu_reference_sample(T=256, layers=1, threads=threads)      # untimed warm-up of the thread pool / autograd
-        dt, tok_s = cpu_reference_sample(T=1024, layers=1, threads=threads)
-        cpu = {"value": tok_s, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"oracle port (torch fp32): 1 full-width LLaMA-3-8B layer fwd+bwd, B=1, T=1024 in {dt:.1f} s on "
-                         f"{threads} of {os.cpu_count()} host threads (fastest of a 1-second thread-count calibration); "
-                         "extrapolated by algorithmic-FLOP ratio to the 32-layer step"}
+        cpu = cpu_train_baseline(T)
+        if not args.no_decode:
+            cpu_decode = cpu_decode_baseline()
 
     decode = None
     if rank == 0 and world == 1 and not args.no_decode:
         try:
             decode = decode_bench(model, dev, peaks)
+            decode["cpu_baseline"] = cpu_decode
         except Exception as e:  # noqa: BLE001 - secondary metric must not lose the headline line
             decode = {"error": repr(e)[:300]}
 

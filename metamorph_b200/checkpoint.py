@@ -219,32 +219,71 @@ def load_mm_projector(model, path: str):
         path = os.path.join(path, "mm_projector.bin")
     weights = torch.load(path, map_location="cpu")
     dtype = next(model.parameters()).dtype
-    return model.load_state_dict({k: v.to(dtype) for k, v in weights.items()}, strict=False)
+    res = model.load_state_dict({k: v.to(dtype) for k, v in weights.items()}, strict=False)
+    # the artefact holds only the projector (+ embeddings with mm_use_im_start_end): what matters is that every tensor in
+    # it found its parameter and that the projector itself is complete
+    bad = [k for k in res.unexpected_keys]
+    lacking = [k for k in res.missing_keys if k.startswith("model.mm_projector.")]
+    if bad or lacking:
+        raise RuntimeError(f"load_mm_projector({path}): unexpected tensors {bad[:4]}, projector tensors missing {lacking[:4]}")
+    return res
 
 
 # --------------------------------------------------------------------------------------------- training checkpoints
+def _opt_items(engine) -> Iterator[Tuple[str, torch.Tensor, torch.Tensor, torch.Tensor]]:
+    """(key, master, exp_avg, exp_avg_sq). With the whole state on the rank (1 GPU, or shard_optimizer=False) the keys are
+    this framework's fused parameter names; with the state sharded over ranks (engine/trainer.py) a bucket contributes
+    this rank's slice under `<bucket>::slice<r>of<w>` and the small replicated tensors are written by rank 0 only."""
+    if engine.shard_world == 1:
+        for name, st in engine.opt.items():
+            yield name, st.p32, st.m, st.v
+        return
+    for b in list(engine.layer_buckets) + list(engine.big_buckets.values()):
+        yield f"{b.name}::slice{engine.shard_rank}of{engine.shard_world}", b.p32, b.m, b.v
+    if engine.rank == 0:
+        for name, st in engine.small_state.items():
+            yield name, st.p32, st.m, st.v
+
+
 def _opt_pairs(engine) -> Iterator[Tuple[str, torch.Tensor]]:
-    for name, st in engine.opt.items():
-        yield name + "::master", st.p32.detach().cpu().contiguous()
-        yield name + "::exp_avg", st.m.detach().cpu().contiguous()
-        yield name + "::exp_avg_sq", st.v.detach().cpu().contiguous()
+    for name, p32, m, v in _opt_items(engine):
+        yield name + "::master", p32.detach().cpu().contiguous()
+        yield name + "::exp_avg", m.detach().cpu().contiguous()
+        yield name + "::exp_avg_sq", v.detach().cpu().contiguous()
+
+
+def _rank_opt_file(rank: int, world: int) -> str:
+    return f"optimizer-rank{rank:05d}-of-{world:05d}.safetensors"
 
 
 def save_training_checkpoint(engine, output_dir: str, max_shard_size="5GB") -> str:
     """`output_dir/checkpoint-<step>/`: HF-format weights (as the reference's Trainer checkpoints) + optimizer state
-    (fp32 master weights, exp_avg, exp_avg_sq under this framework's fused parameter names) + trainer_state.json."""
+    (fp32 master weights, exp_avg, exp_avg_sq under this framework's fused parameter names) + trainer_state.json.
+    With a sharded optimizer EVERY rank must call this: rank 0 writes the weights and trainer_state.json, each rank its
+    own `optimizer-rank*-of-*.safetensors` (as DeepSpeed ZeRO writes one optimizer file per rank); resuming then needs
+    the same world size."""
     ckpt = os.path.join(output_dir, f"{PREFIX_CHECKPOINT_DIR}-{engine.step_count}")
-    save_model(engine.model, ckpt, max_shard_size)
-    sizes = [(f"{n}::{part}", st.p32.numel() * 4) for n, st in engine.opt.items()
-             for part in ("master", "exp_avg", "exp_avg_sq")]
-    _write_sharded(_opt_pairs(engine), sizes, ckpt, max_shard_size, "optimizer.safetensors", OPT_PATTERN, OPT_INDEX_NAME)
-    state = {"global_step": engine.step_count, "max_steps": engine.total_steps, "learning_rate": engine.lr,
-             "warmup_ratio": engine.warmup_ratio, "constant_lr": engine.constant_lr, "betas": list(engine.betas),
-             "eps": engine.eps, "weight_decay": engine.wd, "max_grad_norm": engine.max_grad_norm,
-             "world_size": engine.world}
-    with open(os.path.join(ckpt, TRAINER_STATE_NAME), "w") as fh:
-        json.dump(state, fh, indent=2, sort_keys=True)
-        fh.write("\n")
+    if engine.rank == 0:
+        save_model(engine.model, ckpt, max_shard_size)
+    os.makedirs(ckpt, exist_ok=True)
+    if engine.shard_world == 1:
+        if engine.rank == 0:
+            sizes = [(f"{n}::{part}", p32.numel() * 4) for n, p32, _, _ in _opt_items(engine)
+                     for part in ("master", "exp_avg", "exp_avg_sq")]
+            _write_sharded(_opt_pairs(engine), sizes, ckpt, max_shard_size, "optimizer.safetensors", OPT_PATTERN,
+                           OPT_INDEX_NAME)
+    else:
+        from safetensors.torch import save_file
+        save_file(dict(_opt_pairs(engine)), os.path.join(ckpt, _rank_opt_file(engine.shard_rank, engine.shard_world)))
+    if engine.rank == 0:
+        state = {"global_step": engine.step_count, "max_steps": engine.total_steps, "learning_rate": engine.lr,
+                 "warmup_ratio": engine.warmup_ratio, "constant_lr": engine.constant_lr, "betas": list(engine.betas),
+                 "eps": engine.eps, "weight_decay": engine.wd, "max_grad_norm": engine.max_grad_norm,
+                 "world_size": engine.world, "optimizer_shards": engine.shard_world,
+                 "gradient_accumulation_steps": engine.accum}
+        with open(os.path.join(ckpt, TRAINER_STATE_NAME), "w") as fh:
+            json.dump(state, fh, indent=2, sort_keys=True)
+            fh.write("\n")
     return ckpt
 
 
@@ -267,28 +306,44 @@ def load_training_checkpoint(engine, ckpt_dir: str) -> int:
     from safetensors.torch import load_file
     with open(os.path.join(ckpt_dir, TRAINER_STATE_NAME)) as fh:
         state = json.load(fh)
-    engine.model.load_state_dict(load_model_state(ckpt_dir), strict=False)
-    idx = os.path.join(ckpt_dir, OPT_INDEX_NAME)
-    if os.path.exists(idx):
-        with open(idx) as fh:
-            files = sorted(set(json.load(fh)["weight_map"].values()))
+    res = engine.model.load_state_dict(load_model_state(ckpt_dir), strict=False)
+    engine.model.check_loaded_keys(res, f"load_training_checkpoint({ckpt_dir})")
+    trainable_missing = [k for k in res.missing_keys if k in set(engine.trainable_names)]
+    if trainable_missing:
+        raise RuntimeError(f"load_training_checkpoint({ckpt_dir}): trainable tensors missing: {trainable_missing[:4]}")
+    dests = {}
+    for name, p32, m, v in _opt_items(engine):
+        dests[name] = {"master": p32, "exp_avg": m, "exp_avg_sq": v}
+    if engine.shard_world > 1:
+        if int(state.get("optimizer_shards", 1)) != engine.shard_world:
+            raise RuntimeError(f"{ckpt_dir} holds {state.get('optimizer_shards', 1)} optimizer shard(s); resuming a sharded "
+                               f"optimizer needs the same world size (now {engine.shard_world})")
+        for name, st in engine.small_state.items():            # replicated tensors live in rank 0's file
+            dests[name] = {"master": st.p32, "exp_avg": st.m, "exp_avg_sq": st.v}
+        files = sorted({_rank_opt_file(engine.shard_rank, engine.shard_world), _rank_opt_file(0, engine.shard_world)})
     else:
-        files = ["optimizer.safetensors"]
+        idx = os.path.join(ckpt_dir, OPT_INDEX_NAME)
+        if os.path.exists(idx):
+            with open(idx) as fh:
+                files = sorted(set(json.load(fh)["weight_map"].values()))
+        else:
+            files = ["optimizer.safetensors"]
     seen = set()
     for f in files:
         for key, t in load_file(os.path.join(ckpt_dir, f)).items():
             name, part = key.rsplit("::", 1)
-            st = engine.opt.get(name)
-            if st is None:
+            d = dests.get(name)
+            if d is None:
+                if engine.shard_world > 1 and "::slice" in name:
+                    continue                                    # another rank's slice in rank 0's file
                 raise KeyError(f"optimizer state for unknown parameter {name!r}")
-            dst = {"master": st.p32, "exp_avg": st.m, "exp_avg_sq": st.v}[part]
+            dst = d[part]
             dst.copy_(t.to(dst.device).view_as(dst))
-            if part == "master":
-                st.p16.copy_(dst.to(st.p16.dtype))      # the compute copy is the rounded master, as after every step
             seen.add((name, part))
-    missing = [n for n in engine.opt if (n, "master") not in seen]
+    missing = [n for n in dests if (n, "master") not in seen]
     if missing:
         raise KeyError(f"optimizer state missing for {missing[:3]}... ({len(missing)} parameters)")
+    engine.refresh_compute_copies()      # the bf16 compute copies are the rounded masters, as after every step
     engine.step_count = int(state["global_step"])
     tower = engine.model.get_vision_tower()
     if tower is not None and tower.is_loaded:

@@ -639,7 +639,7 @@ struct TcBwdParams {
   long long lddk, lddv;
   int B, T, Hq, Hkv;
   float scale;
-  int dbg;  // timing experiments only (MM_ATTN_DBG): 1 skip dQ reds, 2 skip dS smem stores, 4 skip exp2, 8 skip MMA drain
+  int Tp;   // row pitch of lse / delta: T rounded up to whole 128-query tiles
 };
 
 // 1-D bulk copy global -> shared, completion counted on an mbarrier
@@ -729,7 +729,7 @@ flash_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       mbar_wait(empty, (uint32_t)((use & 1) ^ 1));
       mbar_arrive_expect_tx(full, 2 * BT_TILE + 1024);
       {
-        const long long off = ((long long)b * p.Hq + hq) * p.T + q0;
+        const long long off = ((long long)b * p.Hq + hq) * p.Tp + q0;
         bulk_load(uStat + buf * 1024, p.lse + off, 512, full);
         bulk_load(uStat + buf * 1024 + 512, p.delta + off, 512, full);
       }
@@ -767,11 +767,9 @@ flash_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       for (int k = 0; k < 8; ++k)
         umma_bf16_ts(tDK, tDPT + (uint32_t)k * 8u, desc_mnmajor(sQ[buf], k), idesc_kmn, (it | k) != 0 ? 1u : 0u);
       // dQ overwrites tST, whose first 64 columns hold P^T (read by the dV MMAs): drain them first
-      if (!(p.dbg & 8)) {
-        umma_commit(mma_sync);
-        mbar_wait(mma_sync, ph);
-        tcgen05_fence_after();
-      }
+      umma_commit(mma_sync);
+      mbar_wait(mma_sync, ph);
+      tcgen05_fence_after();
 #pragma unroll
       for (int k = 0; k < 8; ++k)
         umma_bf16_ss(tST, desc_mnmajor(sdS, k), desc_mnmajor(sK, k), idesc_mnmn, k != 0 ? 1u : 0u);
@@ -853,7 +851,7 @@ flash_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
               const bool ok = key_ok && (q_idx < p.T) && (key_idx <= q_idx);
               const float e = ok ? fast_exp2(fmaf(__uint_as_float(sv[t + u]), sl2, -sLse[qq])) : 0.f;
               pv[u] = e;
-              dvv[u] = e * fmaf(__uint_as_float(dv_[t + u]), p.scale, -sDelta[qq]);
+              dvv[u] = ok ? e * fmaf(__uint_as_float(dv_[t + u]), p.scale, -sDelta[qq]) : 0.f;   // pad statistics are undefined
             }
             pp[t >> 1] = pack_bf16x2(pv[0], pv[1]);
             dd[t >> 1] = pack_bf16x2(dvv[0], dvv[1]);
@@ -890,7 +888,7 @@ flash_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(dq_empty);   // tST may be overwritten by the next S^T
-      if (q_idx < p.T && !(p.dbg & 1)) {
+      if (q_idx < p.T) {
 #pragma unroll
         for (int t = 0; t < 32; t += 4)
           red_add_v4(dq_row + t, __uint_as_float(v[t]), __uint_as_float(v[t + 1]), __uint_as_float(v[t + 2]),
@@ -946,11 +944,11 @@ MM_API int mm_attn_bwd_tc(const void* q, const void* k, const void* v, const voi
                           float scale, void* workspace, long long workspace_bytes, cudaStream_t stream) {
   MM_CHECK_ARG(head_dim == 128, "mm_attn_bwd_tc: head_dim must be 128");
   MM_CHECK_ARG(B > 0 && T > 0 && Hq % Hkv == 0, "mm_attn_bwd_tc: bad shape");
-  const long long delta_bytes = ((long long)B * Hq * T * 4 + 255) / 256 * 256;
+  const int Tp = (T + 127) / 128 * 128;
+  const long long delta_bytes = ((long long)B * Hq * Tp * 4 + 255) / 256 * 256;
   MM_CHECK_ARG(workspace != nullptr &&
                    workspace_bytes >= 2 * delta_bytes + (long long)B * T * Hq * 128 * 4 + 1024,
                "mm_attn_bwd_tc: workspace too small (use mm_attn_bwd_workspace_bytes)");
-  MM_CHECK_ARG(T % 4 == 0, "mm_attn_bwd_tc: T must be a multiple of 4 (16-byte aligned statistics rows)");
   MM_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && lddo % 8 == 0 && lddq % 8 == 0 &&
                    lddk % 8 == 0 && lddv % 8 == 0, "mm_attn_bwd_tc: pitches %% 8");
   float* delta = reinterpret_cast<float*>(workspace);
@@ -958,7 +956,7 @@ MM_API int mm_attn_bwd_tc(const void* q, const void* k, const void* v, const voi
   MM_CHECK_CUDA(cudaMemsetAsync(dq_accum, 0, (size_t)B * T * Hq * 128 * 4, stream));
   float* lse2 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(dq_accum) + (size_t)B * T * Hq * 128 * 4);
   int rc;
-  if ((rc = mm_attn_bwd_delta_launch(o, dout, delta, ldo, lddo, B, T, Hq, head_dim, scale, lse, lse2, stream)))
+  if ((rc = mm_attn_bwd_delta_launch(o, dout, delta, ldo, lddo, B, T, Hq, head_dim, scale, lse, lse2, Tp, stream)))
     return rc;
   CUtensorMap tq, tk, tv, tdo;
   if ((rc = make_tmap_rows(&tq, q, (long long)Hq * 128, (long long)B * T, ldq))) return rc;
@@ -974,10 +972,7 @@ MM_API int mm_attn_bwd_tc(const void* q, const void* k, const void* v, const voi
   TcBwdParams p;
   p.lse = lse2; p.delta = delta; p.dq_accum = dq_accum; p.dk = (bf16*)dk; p.dv = (bf16*)dv; p.seqlens = seqlens;
   p.lddk = lddk; p.lddv = lddv; p.B = B; p.T = T; p.Hq = Hq; p.Hkv = Hkv; p.scale = scale;
-  {
-    const char* e = getenv("MM_ATTN_DBG");
-    p.dbg = e ? atoi(e) : 0;
-  }
+  p.Tp = Tp;
   dim3 grid(Hkv * B, (T + 127) / 128);
   flash_bwd_tc_kernel<<<grid, BT_THREADS, BT_SMEM, stream>>>(tq, tk, tv, tdo, p);
   MM_CHECK_LAUNCH();

@@ -57,7 +57,7 @@ int mm_pdl_enabled();
 int mm_pdl_mode();
 int mm_attn_bwd_delta_launch(const void* o, const void* dout, float* delta, long long ldo, long long lddo,
                              int B, int T, int Hq, int head_dim, float delta_scale, const float* lse,
-                             float* lse2, cudaStream_t stream);
+                             float* lse2, int Tp, cudaStream_t stream);
 int mm_attn_bwd_convert_launch(const float* dq_accum, void* dq, long long R, int C, long long lddq,
                                cudaStream_t stream);
 

@@ -54,7 +54,11 @@ class DecodeEngine:
             prompt_lens = torch.full((B,), P, dtype=torch.int32)
         prompt_lens_dev = prompt_lens.to(dev, dtype=torch.int32)
         eos = list(eos_token_id) if isinstance(eos_token_id, (list, tuple)) else [eos_token_id]
-        eos0, eos1 = eos[0], (eos[1] if len(eos) > 1 else eos[0])
+        if len(eos) > 2:
+            raise NotImplementedError("at most two EOS ids (the reference's default is [128001, 128009])")
+        # an empty list never matches (token ids are >= 0), like `next_token.item() in []` (metamorph_llama.py:583)
+        eos0 = eos[0] if eos else -1
+        eos1 = eos[1] if len(eos) > 1 else eos0
 
         kc = torch.zeros((L, B, Hkv, Tmax, dh), dtype=torch.bfloat16, device=dev)
         vc = torch.zeros_like(kc)

@@ -28,13 +28,15 @@ class GradProvider:
     def __init__(self, model):
         self.model = model
         self.buffers: Dict[str, torch.Tensor] = {}
+        # True while a later micro-batch of a gradient-accumulation window runs: destinations are added to, not overwritten
+        self.accumulate = False
 
     def get(self, name: str, like: torch.Tensor, fp32: bool = False, zero: bool = False) -> torch.Tensor:
         buf = self.buffers.get(name)
         if buf is None:
             buf = torch.zeros(like.shape, dtype=torch.float32 if fp32 else like.dtype, device=like.device)
             self.buffers[name] = buf
-        elif zero:
+        elif zero and not self.accumulate:
             buf.zero_()
         return buf
 
@@ -52,7 +54,7 @@ class GradProvider:
     def layer_done(self, i: int, g: LayerGrads):  # hook for fused optimizers / gradient collectives
         pass
 
-    def group_done(self, group: str):
+    def group_done(self, group: str, written=None):
         pass
 
 
@@ -88,7 +90,8 @@ class HotPath:
     # ------------------------------------------------------------------ heads + losses (A6, A7)
     def heads(self, hidden: torch.Tensor, plan: InterleavePlan, labels: Optional[torch.Tensor],
               targets: Optional[torch.Tensor], want_grad: bool, want_logits: bool,
-              grads: Optional[GradProvider], use_vision_ar: bool, vision_coef: float) -> HeadResult:
+              grads: Optional[GradProvider], use_vision_ar: bool, vision_coef: float,
+              train_lm_head: bool = True, train_vision_head: bool = True) -> HeadResult:
         """hidden: final-norm output [B*T, H]. Reproduces metamorph_llama.py:398-474."""
         m = self.m
         B, T = plan.batch, plan.seq_len
@@ -145,9 +148,13 @@ class HotPath:
         Ms = h_src.shape[0]
         d_hidden = None
         d_src = None
+        acc = bool(want_grad and grads.accumulate)
+        written = []
         if want_grad:
             d_src = torch.empty_like(h_src)
-            g_lm = grads.get("lm_head.weight", m.lm_head.weight, fp32=True)
+            if train_lm_head:
+                g_lm = grads.get("lm_head.weight", m.lm_head.weight, fp32=True)
+                written.append("lm_head.weight")
         R = self.ce_chunk_rows
         for r0 in range(0, Ms, R):
             r1 = min(Ms, r0 + R)
@@ -162,8 +169,9 @@ class HotPath:
                 dl = torch.empty((r1 - r0, ldv), dtype=torch.bfloat16, device=dev)
                 ops.ce_fwd_bwd(lg, lab_src[r0:r1], V, loss_lang, dlogits=dl, grad_scale=ce_scale * ce_grad_mult)
                 ops.gemm(dl[:, :V], m.lm_head.weight.data, b_mn=True, out=d_src[r0:r1])
-                ops.gemm(dl[:, :V], hs, a_mn=True, b_mn=True, out=g_lm, out_dtype=torch.float32,
-                         accumulate=(r0 > 0))
+                if train_lm_head:
+                    ops.gemm(dl[:, :V], hs, a_mn=True, b_mn=True, out=g_lm, out_dtype=torch.float32,
+                             accumulate=(r0 > 0 or acc))
                 del dl
             else:
                 ops.ce_fwd_bwd(lg, lab_src[r0:r1], V, loss_lang)
@@ -196,10 +204,13 @@ class HotPath:
                 else:
                     raise NotImplementedError("only normalize_vision=True (cosine loss) is in scope")
                 if want_grad and use_vision_ar:
-                    vg = {k: grads.get("vision_head." + k, _param(vh, k), fp32=k.endswith("bias"),
-                                       zero=k.endswith("bias"))
-                          for k in ("0.weight", "0.bias", "2.weight", "2.bias")}
-                    dh_sel = vh.backward_train(vh_saved, dpred, vg, need_dx=True)
+                    vg = None
+                    if train_vision_head:
+                        vg = {k: grads.get("vision_head." + k, _param(vh, k), fp32=k.endswith("bias"),
+                                           zero=k.endswith("bias"))
+                              for k in ("0.weight", "0.bias", "2.weight", "2.bias")}
+                        written += ["vision_head." + k for k in vg]
+                    dh_sel = vh.backward_train(vh_saved, dpred, vg, need_dx=True, accumulate=acc)
                     ops.scatter_add_rows_(d_hidden, rows, dh_sel)
             else:
                 # reference: mean over zero rows -> NaN, and NaN != 0 so it is added to the loss
@@ -210,14 +221,17 @@ class HotPath:
             # reference adds the image loss unless it is exactly 0 (metamorph_llama.py:470-474)
             loss = loss + vision_coef * loss_img
         if want_grad:
-            grads.group_done("heads")
+            # only the buffers written in THIS pass: a step without answer images gives the vision head no gradient (as
+            # in the reference), so a stale buffer of an earlier step must not reach the optimizer
+            grads.group_done("heads", written=written)
         return HeadResult(loss.reshape(()), loss_lang, loss_img, d_hidden,
                           logits_full.view(B, T, V) if want_logits else None)
 
     # ------------------------------------------------------------------ full step pieces
     def forward_backward(self, plan: InterleavePlan, images, grads: Optional[GradProvider],
                          want_grad: bool, want_logits: bool = False, n_save_gu: int = 0,
-                         train_embed: bool = True, train_projector: bool = True):
+                         train_embed: bool = True, train_projector: bool = True, train_llm: bool = True,
+                         train_lm_head: bool = True, train_vision_head: bool = True):
         """One pass of the hot path over one batch. Returns HeadResult (+ last hidden)."""
         m = self.m
         model = m.get_model()
@@ -245,14 +259,19 @@ class HotPath:
         hidden = stack.forward(layers, model.norm.weight.data, x, ctx, save=want_grad, n_save_gu=n_save_gu)
         del x
         res = self.heads(hidden, plan, plan.labels, targets, want_grad, want_logits, grads,
-                         m.use_vision_ar, m.vision_coef)
+                         m.use_vision_ar, m.vision_coef, train_lm_head=train_lm_head,
+                         train_vision_head=train_vision_head)
         if not want_grad:
             return res, hidden
-        g_norm = grads.get("model.norm.weight", model.norm.weight, fp32=True, zero=True)
+        acc = grads.accumulate
+        g_norm = grads.get("model.norm.weight", model.norm.weight, fp32=True, zero=True) if train_llm else None
         dx = stack.final_norm_backward(model.norm.weight.data, res.d_hidden, ctx, g_norm)
         res.d_hidden = None
-        grads.group_done("final_norm")
-        dx = stack.backward(layers, grads.layer, dx, ctx, on_layer_done=grads.layer_done)
+        if train_llm:
+            grads.group_done("final_norm")
+            dx = stack.backward(layers, grads.layer, dx, ctx, on_layer_done=grads.layer_done, accumulate=acc)
+        else:   # frozen language model (stage 1): only the dgrad chain runs, no wgrad GEMM / norm-weight reduction
+            dx = stack.backward(layers, None, dx, ctx, need_wgrad=False)
         # d(inputs_embeds) -> embedding table + projector output
         d_embed = grads.get("model.embed_tokens.weight", model.embed_tokens.weight, zero=True) if train_embed else None
         d_img = torch.empty_like(ar_feats) if train_projector else None
@@ -267,6 +286,6 @@ class HotPath:
             pg = {k: grads.get("model.mm_projector." + k, _param(pj, k), fp32=k.endswith("bias"),
                                zero=k.endswith("bias"))
                   for k in ("0.weight", "0.bias", "2.weight", "2.bias")}
-            pj.backward_train(proj_saved, d_img, pg, need_dx=False)
+            pj.backward_train(proj_saved, d_img, pg, need_dx=False, accumulate=acc)
             grads.group_done("projector")
         return res, hidden

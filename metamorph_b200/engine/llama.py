@@ -170,8 +170,8 @@ class LlamaStack:
     def final_norm_backward(self, final_norm, dh_final, ctx: StackContext, dw_accum):
         return ops.rmsnorm_bwd(dh_final, ctx.x_final_in, final_norm, self.dims.rms_eps, dw_accum=dw_accum)
 
-    def layer_backward(self, w: LayerWeights, g: LayerGrads, s: LayerSaved, dx_out: torch.Tensor,
-                       ctx: StackContext, accumulate: bool = False) -> torch.Tensor:
+    def layer_backward(self, w: LayerWeights, g: Optional[LayerGrads], s: LayerSaved, dx_out: torch.Tensor,
+                       ctx: StackContext, accumulate: bool = False, need_wgrad: bool = True) -> torch.Tensor:
         d = self.dims
         B, T = ctx.B, ctx.T
         Hq, Hkv, dh = d.n_heads, d.n_kv_heads, d.head_dim
@@ -188,16 +188,19 @@ class LlamaStack:
         # gu <- d(gate|up) in place, act = silu(g)*u recomputed for the down_proj wgrad
         act = torch.empty((M, d.intermediate), dtype=torch.bfloat16, device=dx_out.device)
         ops.gemm(dx_out, w.wd, b_mn=True, out=act, aux=gu, epilogue=ops.EPI_SWIGLU_BWD)
-        ops.gemm(dx_out, act, a_mn=True, b_mn=True, out=g.wd, accumulate=accumulate)   # dWd = dout^T act
+        if need_wgrad:
+            ops.gemm(dx_out, act, a_mn=True, b_mn=True, out=g.wd, accumulate=accumulate)   # dWd = dout^T act
         del act
-        ops.gemm(gu, n2, a_mn=True, b_mn=True, out=g.wgu, accumulate=accumulate)       # dWgu = dgu^T n2
+        if need_wgrad:
+            ops.gemm(gu, n2, a_mn=True, b_mn=True, out=g.wgu, accumulate=accumulate)       # dWgu = dgu^T n2
         dn2 = ops.gemm(gu, w.wgu, b_mn=True)                                            # [M, H]
         del gu, n2
         s.gu = None
-        dh_mid = ops.rmsnorm_bwd(dn2, s.h_mid, w.ln2, d.rms_eps, dres_in=dx_out, dw_accum=g.ln2)
+        dh_mid = ops.rmsnorm_bwd(dn2, s.h_mid, w.ln2, d.rms_eps, dres_in=dx_out, dw_accum=g.ln2 if need_wgrad else None)
         del dn2
         # ---- attention: h_mid = x + o_proj(attn(rope(qkv(norm1(x)))))
-        ops.gemm(dh_mid, s.attn, a_mn=True, b_mn=True, out=g.wo, accumulate=accumulate)  # dWo
+        if need_wgrad:
+            ops.gemm(dh_mid, s.attn, a_mn=True, b_mn=True, out=g.wo, accumulate=accumulate)  # dWo
         dattn = ops.gemm(dh_mid, w.wo, b_mn=True)                                         # [M, Hq*dh]
         q, k, v = s.qkv[:, :Hq * dh], s.qkv[:, Hq * dh:(Hq + Hkv) * dh], s.qkv[:, (Hq + Hkv) * dh:]
         if ctx.segments is None:
@@ -215,24 +218,26 @@ class LlamaStack:
                                              1, n, Hq, Hkv, dh, self.scale, workspace=self._attn_ws)
         del dattn
         ops.rope_(dqkv, ctx.pos, self.cos, self.sin, Hq + Hkv, dh, backward=True)
-        n1 = ops.rmsnorm(s.x_in, w.ln1, d.rms_eps)
-        ops.gemm(dqkv, n1, a_mn=True, b_mn=True, out=g.wqkv, accumulate=accumulate)      # dWqkv
-        del n1
+        if need_wgrad:
+            n1 = ops.rmsnorm(s.x_in, w.ln1, d.rms_eps)
+            ops.gemm(dqkv, n1, a_mn=True, b_mn=True, out=g.wqkv, accumulate=accumulate)      # dWqkv
+            del n1
         dn1 = ops.gemm(dqkv, w.wqkv, b_mn=True)
         del dqkv
-        dx = ops.rmsnorm_bwd(dn1, s.x_in, w.ln1, d.rms_eps, dres_in=dh_mid, dw_accum=g.ln1)
+        dx = ops.rmsnorm_bwd(dn1, s.x_in, w.ln1, d.rms_eps, dres_in=dh_mid, dw_accum=g.ln1 if need_wgrad else None)
         return dx
 
-    def backward(self, layers: List[LayerWeights], grads_for: Callable[[int], LayerGrads],
+    def backward(self, layers: List[LayerWeights], grads_for: Optional[Callable[[int], LayerGrads]],
                  dx: torch.Tensor, ctx: StackContext,
                  on_layer_done: Optional[Callable[[int, LayerGrads], None]] = None,
-                 accumulate: bool = False) -> torch.Tensor:
-        """dx: gradient w.r.t. the last layer's output (i.e. after final_norm_backward)."""
+                 accumulate: bool = False, need_wgrad: bool = True) -> torch.Tensor:
+        """dx: gradient w.r.t. the last layer's output (i.e. after final_norm_backward).
+        need_wgrad=False (frozen stack, e.g. stage-1 projector training): only the dgrad chain runs."""
         for i in reversed(range(len(layers))):
             s = ctx.saved[i]
-            g = grads_for(i)
-            dx = self.layer_backward(layers[i], g, s, dx, ctx, accumulate=accumulate)
+            g = grads_for(i) if need_wgrad else None
+            dx = self.layer_backward(layers[i], g, s, dx, ctx, accumulate=accumulate, need_wgrad=need_wgrad)
             ctx.saved[i] = None
-            if on_layer_done is not None:
+            if need_wgrad and on_layer_done is not None:
                 on_layer_done(i, g)
         return dx

@@ -59,7 +59,10 @@ class ContinuousBatcher:
         self.ntok = model.get_vision_tower().image_token_len if model.get_vision_tower() is not None else 0
         self.C = model.vision_head.fc2.out_features
         eos = list(eos_token_id) if isinstance(eos_token_id, (list, tuple)) else [eos_token_id]
-        self.eos0, self.eos1 = eos[0], (eos[1] if len(eos) > 1 else eos[0])
+        if len(eos) > 2:
+            raise NotImplementedError("at most two EOS ids (the reference's default is [128001, 128009])")
+        self.eos0 = eos[0] if eos else -1                       # an empty list never matches
+        self.eos1 = eos[1] if len(eos) > 1 else self.eos0
         self.start_id, self.end_id = start_image_token_id, end_image_token_id
         self.stack.ensure_positions(max_context + 1)
         self.kc = torch.zeros((self.L, B, d.n_kv_heads, max_context, d.head_dim), dtype=torch.bfloat16, device=dev)

@@ -1,21 +1,35 @@
-"""Train step driver: hot path forward/backward + fused AdamW + data-parallel gradient collective.
+"""Train step driver: hot path forward/backward + fused AdamW + the data-parallel gradient collective.
 
-Replaces, for this path, HF Trainer + Accelerate + DeepSpeed ZeRO (scripts/zero2.json):
-  * pure data parallel, one process per GPU (torchrun), NCCL over NVLink/NVSwitch;
-  * "optimizer in the backward sweep": as soon as a layer's wgrad GEMMs retire, its gradient
-    bucket (one flat bf16 buffer, ~436 MB for LLaMA-3-8B) is all-reduced on a dedicated comm stream
-    and the fused AdamW kernel updates that layer's fp32 master weights / moments / bf16 copy, while
-    the main stream continues with the next layer's backward. Only two layer-sized gradient buckets
-    exist, so the 16 GB of full-model gradients are never resident (180 GB HBM budget);
-  * optional global-norm clipping (`max_grad_norm`) switches to a two-phase step with resident
-    gradients (the reference scripts pass no max_grad_norm).
-Optimizer = torch.optim.AdamW semantics (reference: --optim adamw_torch, train.py:82), cosine LR with
-3 % warm-up (scripts/*.sh: lr_scheduler_type cosine, warmup_ratio 0.03), weight decay 0.
+Replaces, for this path, HF Trainer + Accelerate + DeepSpeed ZeRO-2 (scripts/zero2.json:16-24:
+`stage 2`, `overlap_comm`, `reduce_scatter`, `contiguous_gradients`):
+  * data parallel, one process per GPU (torchrun), NCCL over NVLink/NVSwitch, parameters replicated in bf16;
+  * OPTIMIZER STATE SHARDED (ZeRO-1/2 style): every large tensor group ("bucket": one decoder layer's four matrices in
+    ONE flat bf16 buffer, the embedding table, lm_head) keeps fp32 master weights and both AdamW moments only for this
+    rank's 1/world slice of the flat index space. Per bucket: reduce-scatter of the gradient (the rank receives the SUM
+    of its slice) -> fused AdamW on the slice -> all-gather of the updated bf16 slice straight into the flat parameter
+    buffer every rank computes with. Same wire volume as the all-reduce it replaces; AdamW's HBM traffic and the
+    optimizer memory drop by `world` (8 GPUs: 97 -> 12 GB of state per GPU, which is what lets config 3 run its stated
+    8 samples per GPU). world == 1 is the same code with a slice that is the whole bucket and no collective;
+  * "optimizer in the backward sweep": as soon as a layer's wgrad GEMMs retire, its bucket is reduced and applied on a
+    side stream while the main stream continues with the next layer's backward. Without accumulation only two
+    layer-sized gradient buffers exist (they rotate), so the 16 GB of full-model gradients are never resident;
+  * `gradient_accumulation_steps` = k (HF TrainingArguments; scripts/*.sh pass it): `step()` takes k micro-batches, the
+    wgrad GEMMs accumulate into resident per-layer gradient buffers (`accumulate` epilogue), and the collective + AdamW
+    run once, during the LAST micro-batch's backward sweep, on the mean over micro-batches (HF divides each micro loss
+    by k);
+  * optional global-norm clipping (`max_grad_norm`): gradients stay resident, the squared norm is summed over the
+    reduce-scattered slices (+ the small replicated tensors once) and the clip factor is applied inside AdamW
+    (the reference scripts pass no max_grad_norm);
+  * parameters that do not train (stage 1, `tune_mm_mlp_adapter`: everything but the projector is frozen,
+    train.py:1516-1519) get no wgrad GEMMs at all — only the dgrad chain down to the projector runs.
+Small tensors (norm weights, projector, vision head: ~45 M parameters) keep replicated state and an all-reduce.
+Optimizer = torch.optim.AdamW semantics (reference: --optim adamw_torch, train.py:82), cosine LR with 3 % warm-up
+(scripts/*.sh: lr_scheduler_type cosine, warmup_ratio 0.03), weight decay 0.
 """
 from __future__ import annotations
 
 import math
-from typing import Dict, List, Optional
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -34,122 +48,277 @@ def cosine_lr(step: int, total_steps: int, base_lr: float, warmup_ratio: float =
     return base_lr * max(0.0, 0.5 * (1.0 + math.cos(math.pi * prog)))
 
 
+def shard_bounds(numel: int, world: int, rank: int) -> Tuple[int, int]:
+    """[lo, hi) of this rank's slice of a flat bucket; numel must be a multiple of 8 * world (16-byte slices)."""
+    assert numel % (8 * world) == 0, f"bucket of {numel} elements cannot be cut into {world} 16-byte-aligned slices"
+    n = numel // world
+    return rank * n, (rank + 1) * n
+
+
 class _OptState:
+    """fp32 master / exp_avg / exp_avg_sq of ONE parameter tensor, as views into its bucket's state when the whole
+    tensor lies inside this rank's slice (always at world == 1), standalone tensors for replicated small parameters."""
     __slots__ = ("p16", "p32", "m", "v")
 
-    def __init__(self, p: torch.Tensor):
-        self.p16 = p.data
-        self.p32 = p.data.float()
+    def __init__(self, p16, p32, m, v):
+        self.p16, self.p32, self.m, self.v = p16, p32, m, v
+
+
+class ShardedBucket:
+    """One flat bf16 parameter buffer (the tensors' `.data` are views into it) + this rank's slice of the optimizer state."""
+
+    def __init__(self, name: str, params: Sequence[Tuple[str, torch.nn.Parameter]], world: int, rank: int,
+                 grad_dtype=torch.bfloat16):
+        self.name, self.world, self.rank = name, world, rank
+        self.names = [n for n, _ in params]
+        self.shapes = [tuple(p.shape) for _, p in params]
+        self.sizes = [p.numel() for _, p in params]
+        self.numel = sum(self.sizes)
+        self.grad_dtype = grad_dtype
+        dev = params[0][1].device
+        if len(params) == 1 and params[0][1].data.is_contiguous():
+            self.flat = params[0][1].data.view(-1)                       # a single tensor is its own flat buffer
+        else:
+            self.flat = torch.empty(self.numel, dtype=torch.bfloat16, device=dev)
+            off = 0
+            for (_, p), n in zip(params, self.sizes):
+                self.flat[off:off + n].copy_(p.data.reshape(-1))
+                p.data = self.flat[off:off + n].view(p.shape)          # the model now computes with views of the bucket
+                off += n
+        self.lo, self.hi = shard_bounds(self.numel, world, rank)
+        sl = self.flat[self.lo:self.hi]
+        self.p32 = sl.float()
         self.m = torch.zeros_like(self.p32)
         self.v = torch.zeros_like(self.p32)
+        # staging for the collectives (world > 1): the reduced gradient slice and the updated bf16 slice
+        self.gshard = torch.empty(self.hi - self.lo, dtype=grad_dtype, device=dev) if world > 1 else None
+        self.pshard = torch.empty(self.hi - self.lo, dtype=torch.bfloat16, device=dev) if world > 1 else None
+
+    def param_views(self) -> Dict[str, _OptState]:
+        """Per-tensor views of the state for tensors that lie entirely inside this rank's slice."""
+        out, off = {}, 0
+        for n, shp, sz in zip(self.names, self.shapes, self.sizes):
+            if off >= self.lo and off + sz <= self.hi:
+                a, b = off - self.lo, off - self.lo + sz
+                out[n] = _OptState(self.flat[off:off + sz].view(shp), self.p32[a:b].view(shp), self.m[a:b].view(shp),
+                                   self.v[a:b].view(shp))
+            off += sz
+        return out
+
+    def grad_views(self, flat_grad: torch.Tensor) -> List[torch.Tensor]:
+        views, off = [], 0
+        for shp, sz in zip(self.shapes, self.sizes):
+            views.append(flat_grad[off:off + sz].view(shp))
+            off += sz
+        return views
 
 
-class FusedGradProvider(GradProvider):
-    """Gradient buckets + immediate (all-reduce ->) AdamW as each bucket completes."""
+class BucketGradProvider(GradProvider):
+    """Hands the hot path its gradient destinations and fires a bucket's collective + AdamW as soon as it is complete.
 
-    def __init__(self, model, engine: "TrainEngine"):
+    rotating mode (no accumulation, no clipping): two layer-sized flat buffers alternate between layers;
+    resident mode: one flat buffer per layer (needed to accumulate over micro-batches / to clip by the global norm)."""
+
+    def __init__(self, model, engine: "TrainEngine", resident: bool):
         super().__init__(model)
         self.e = engine
-        l0 = model.model.layers[0]
-        self.shapes = [l0.self_attn.qkv_proj.weight.shape, l0.self_attn.o_proj.weight.shape,
-                       l0.mlp.gate_up_proj.weight.shape, l0.mlp.down_proj.weight.shape]
-        self.sizes = [s[0] * s[1] for s in self.shapes]
-        dev = l0.self_attn.qkv_proj.weight.device
-        H = l0.input_layernorm.weight.shape[0]
-        n = sum(self.sizes)
-        self.sets = []
-        for _ in range(2):
-            flat = torch.zeros(n, dtype=torch.bfloat16, device=dev)
-            ln = torch.zeros(2 * H, dtype=torch.float32, device=dev)
-            self.sets.append(dict(flat=flat, ln=ln, free=None))
-        self.H = H
+        self.resident = resident
+        self.apply_now = True          # False during all but the last micro-batch of an accumulation window
+        self.defer = False             # clipping: collect everything, apply at the end of the step
+        self.pending: List = []
+        lb = engine.layer_buckets
+        self.H = model.model.layers[0].input_layernorm.weight.shape[0]
+        dev = model.device
+        if lb:
+            n_sets = len(lb) if resident else min(2, len(lb))
+            self.sets = [dict(flat=torch.zeros(lb[0].numel, dtype=torch.bfloat16, device=dev),
+                              ln=torch.zeros(2 * self.H, dtype=torch.float32, device=dev), free=None)
+                         for _ in range(n_sets)]
+        else:
+            self.sets = []
+
+    def _set(self, i: int):
+        return self.sets[i if self.resident else i % len(self.sets)]
 
     def layer(self, i: int) -> LayerGrads:
-        s = self.sets[i % 2]
+        s = self._set(i)
         if s["free"] is not None:                      # bucket still being reduced / applied
             torch.cuda.current_stream().wait_event(s["free"])
             s["free"] = None
-        views, off = [], 0
-        for shp, sz in zip(self.shapes, self.sizes):
-            views.append(s["flat"][off:off + sz].view(shp))
-            off += sz
-        s["ln"].zero_()
-        return LayerGrads(views[0], views[1], views[2], views[3], s["ln"][:self.H], s["ln"][self.H:])
+        v = self.e.layer_buckets[i].grad_views(s["flat"])
+        if not self.accumulate:
+            s["ln"].zero_()
+        return LayerGrads(v[0], v[1], v[2], v[3], s["ln"][:self.H], s["ln"][self.H:])
 
     def layer_done(self, i: int, g: LayerGrads):
-        s = self.sets[i % 2]
+        if not self.apply_now:
+            return
+        s = self._set(i)
         l = self.model.model.layers[i]
-        params = [(l.self_attn.qkv_proj.weight, g.wqkv), (l.self_attn.o_proj.weight, g.wo),
-                  (l.mlp.gate_up_proj.weight, g.wgu), (l.mlp.down_proj.weight, g.wd),
-                  (l.input_layernorm.weight, g.ln1), (l.post_attention_layernorm.weight, g.ln2)]
-        s["free"] = self.e.reduce_and_apply(params, [s["flat"], s["ln"]])
+        small = [(l.input_layernorm.weight, g.ln1), (l.post_attention_layernorm.weight, g.ln2)]
+        if self.defer:
+            self.pending.append((self.e.layer_buckets[i], s["flat"], small, [s["ln"]]))
+            return
+        s["free"] = self.e.reduce_and_apply(self.e.layer_buckets[i], s["flat"], small, [s["ln"]])
 
-    def group_done(self, group: str):
-        m = self.model
-        names = {
-            "heads": ["lm_head.weight", "vision_head.0.weight", "vision_head.0.bias", "vision_head.2.weight",
-                      "vision_head.2.bias"],
-            "final_norm": ["model.norm.weight"],
-            "embed": ["model.embed_tokens.weight"],
-            "projector": ["model.mm_projector.0.weight", "model.mm_projector.0.bias",
-                          "model.mm_projector.2.weight", "model.mm_projector.2.bias"],
-        }[group]
+    GROUPS = {
+        "heads": ["lm_head.weight", "vision_head.0.weight", "vision_head.0.bias", "vision_head.2.weight",
+                  "vision_head.2.bias"],
+        "final_norm": ["model.norm.weight"],
+        "embed": ["model.embed_tokens.weight"],
+        "projector": ["model.mm_projector.0.weight", "model.mm_projector.0.bias",
+                      "model.mm_projector.2.weight", "model.mm_projector.2.bias"],
+    }
+
+    def group_done(self, group: str, written: Optional[Sequence[str]] = None):
+        """`written`: the gradient buffers the hot path actually wrote this step (e.g. the vision head has none on a step
+        without answer images) — the others must not be applied: their buffers hold a previous step's gradient, and the
+        reference gives such parameters no gradient at all."""
+        if not self.apply_now:
+            return
+        names = [n for n in self.GROUPS[group] if n in self.buffers and (written is None or n in written)]
         named = self.e.named_params
-        params = [(named[n], self.buffers[n]) for n in names if n in self.buffers and n in self.e.opt]
-        if params:
-            self.e.reduce_and_apply(params, [b for _, b in params])
+        for n in names:
+            if n in self.e.big_buckets:
+                item = (self.e.big_buckets[n], self.buffers[n].view(-1), [], [])
+            elif n in self.e.small_state:
+                item = (None, None, [(named[n], self.buffers[n])], [self.buffers[n]])
+            else:
+                continue
+            if self.defer:
+                self.pending.append(item)
+            else:
+                self.e.reduce_and_apply(*item)
 
 
 class TrainEngine:
     def __init__(self, model, lr: float = 6.93e-5, betas=(0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 0.0, max_grad_norm: Optional[float] = None, total_steps: int = 1000,
                  warmup_ratio: float = 0.03, constant_lr: bool = False, n_save_gu_layers: int = 0,
-                 pack_sequences: bool = False, pack_len: Optional[int] = None):
+                 pack_sequences: bool = False, pack_len: Optional[int] = None,
+                 gradient_accumulation_steps: int = 1, shard_optimizer: bool = True):
         self.model = model
         self.hot = HotPath(model)
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
         self.max_grad_norm = max_grad_norm
         self.total_steps, self.warmup_ratio, self.constant_lr = total_steps, warmup_ratio, constant_lr
         self.n_save_gu_layers = n_save_gu_layers
-        # SURVEY §8f N2: lay the samples of a batch end to end (block-diagonal attention) instead of padding them
+        # SURVEY section 8f N2: lay the samples of a batch end to end (block-diagonal attention) instead of padding them
         self.pack_sequences, self.pack_len = pack_sequences, pack_len
+        self.accum = max(1, int(gradient_accumulation_steps))
         self.step_count = 0
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank() if self.world > 1 else 0
+        # shard_optimizer=False keeps the whole state on every rank (slices = whole buckets, all-reduce instead of
+        # reduce-scatter + all-gather): the round-1 behaviour, kept for A/B measurements
+        self.shard_world = self.world if shard_optimizer else 1
+        self.shard_rank = self.rank if shard_optimizer else 0
         self.named_params: Dict[str, torch.nn.Parameter] = dict(model.named_parameters())
+        trainable = {n: p for n, p in self.named_params.items()
+                     if p.requires_grad and "vision_tower" not in n and "vision_proj" not in n}
+
+        # ---- buckets
+        self.layer_buckets: List[ShardedBucket] = []
+        self.big_buckets: Dict[str, ShardedBucket] = {}
+        self.small_state: Dict[str, _OptState] = {}
         self.opt: Dict[str, _OptState] = {}
-        for n, p in self.named_params.items():
-            if p.requires_grad and "vision_tower" not in n and "vision_proj" not in n:
-                self.opt[n] = _OptState(p)
-        self._state_by_ptr = {st.p16.data_ptr(): st for st in self.opt.values()}
-        # side stream: gradient all-reduce (N>1) and the HBM-bound fused AdamW run here, concurrently with
-        # the tensor-core-bound backward GEMMs of the next layers on the main stream
+        L = len(model.model.layers)
+        self.train_llm = all(f"model.layers.{i}.self_attn.qkv_proj.weight" in trainable for i in range(L)) and L > 0
+        claimed = set()
+        if self.train_llm:
+            for i in range(L):
+                p = f"model.layers.{i}."
+                names = [p + "self_attn.qkv_proj.weight", p + "self_attn.o_proj.weight", p + "mlp.gate_up_proj.weight",
+                         p + "mlp.down_proj.weight"]
+                b = ShardedBucket(f"layer{i}", [(n, trainable[n]) for n in names], self.shard_world, self.shard_rank)
+                self.layer_buckets.append(b)
+                claimed.update(names)
+        for n, gd in (("lm_head.weight", torch.float32), ("model.embed_tokens.weight", torch.bfloat16)):
+            if n in trainable and trainable[n].numel() % (8 * self.shard_world) == 0 and trainable[n].numel() >= (1 << 22):
+                self.big_buckets[n] = ShardedBucket(n, [(n, trainable[n])], self.shard_world, self.shard_rank, grad_dtype=gd)
+                claimed.add(n)
+        for n, p in trainable.items():
+            if n not in claimed:
+                p32 = p.data.float()
+                self.small_state[n] = _OptState(p.data, p32, torch.zeros_like(p32), torch.zeros_like(p32))
+        for b in list(self.layer_buckets) + list(self.big_buckets.values()):
+            self.opt.update(b.param_views())
+        self.opt.update(self.small_state)
+        self.trainable_names = list(trainable)
+        self._state_by_ptr = {st.p16.data_ptr(): st for st in self.small_state.values()}
+        # side stream: the gradient collectives (N > 1) and the HBM-bound fused AdamW run here, concurrently with the
+        # tensor-core-bound backward GEMMs of the next layers on the main stream
         self.comm_stream = torch.cuda.Stream()
-        self.provider = FusedGradProvider(model, self) if max_grad_norm is None else GradProvider(model)
+        resident = self.accum > 1 or max_grad_norm is not None
+        self.provider = BucketGradProvider(model, self, resident=resident)
+        self.provider.defer = max_grad_norm is not None
         self.kernel_launch_estimate = 0
 
     # -------------------------------------------------------------- optimizer plumbing
-    def _apply(self, params, lr: float, grad_scale: float, scale_tensor=None):
+    def optimizer_state_bytes(self) -> int:
+        n = sum(b.p32.numel() for b in list(self.layer_buckets) + list(self.big_buckets.values()))
+        n += sum(st.p32.numel() for st in self.small_state.values())
+        return 12 * n
+
+    @torch.no_grad()
+    def refresh_compute_copies(self):
+        """bf16 compute copies <- rounded fp32 masters (after restoring the optimizer state from a checkpoint)."""
+        for b in list(self.layer_buckets) + list(self.big_buckets.values()):
+            if self.shard_world == 1:
+                b.flat.copy_(b.p32)
+            else:
+                b.pshard.copy_(b.p32)
+                dist.all_gather_into_tensor(b.flat, b.pshard)
+        for st in self.small_state.values():
+            st.p16.copy_(st.p32)
+
+    def _adamw(self, p16, p32, m, v, grad, lr, grad_scale, scale_tensor=None):
         b1, b2 = self.betas
+        ops.adamw_step_(p16.reshape(-1), p32.reshape(-1), m.reshape(-1), v.reshape(-1), grad.reshape(-1), lr=lr, beta1=b1,
+                        beta2=b2, eps=self.eps, wd=self.wd, step=self.step_count, grad_scale=grad_scale,
+                        grad_scale_tensor=scale_tensor)
+
+    def _apply_small(self, params, lr, grad_scale, scale_tensor=None):
         for p, g in params:
             st = self._state_by_ptr.get(p.data.data_ptr())
-            if st is None:
-                continue
-            ops.adamw_step_(st.p16.view(-1), st.p32.view(-1), st.m.view(-1), st.v.view(-1), g.reshape(-1),
-                            lr=lr, beta1=b1, beta2=b2, eps=self.eps, wd=self.wd, step=self.step_count,
-                            grad_scale=grad_scale, grad_scale_tensor=scale_tensor)
+            if st is not None:
+                self._adamw(st.p16, st.p32, st.m, st.v, g, lr, grad_scale, scale_tensor)
 
-    def reduce_and_apply(self, params, flat_buffers):
-        """(all-reduce the bucket ->) fused AdamW. Returns an event marking bucket reuse safety."""
+    def _bucket_reduce(self, b: ShardedBucket, flat_grad: torch.Tensor) -> torch.Tensor:
+        """(comm stream) -> this rank's slice of the summed gradient."""
+        if self.world == 1:
+            return flat_grad
+        if self.shard_world == 1:
+            dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
+            return flat_grad
+        dist.reduce_scatter_tensor(b.gshard, flat_grad, op=dist.ReduceOp.SUM)
+        return b.gshard
+
+    def _bucket_update(self, b: ShardedBucket, gslice, lr, grad_scale, scale_tensor=None):
+        """(comm stream) fused AdamW on the slice, then the updated bf16 slice goes back into every rank's flat buffer."""
+        if self.shard_world == 1:
+            self._adamw(b.flat, b.p32, b.m, b.v, gslice, lr, grad_scale, scale_tensor)
+            return
+        self._adamw(b.pshard, b.p32, b.m, b.v, gslice, lr, grad_scale, scale_tensor)
+        dist.all_gather_into_tensor(b.flat, b.pshard)
+
+    def reduce_and_apply(self, bucket: Optional[ShardedBucket], flat_grad, small_params, small_bufs):
+        """Collective + AdamW of one completed bucket (and/or of small replicated tensors) on the side stream.
+        Returns an event marking when the gradient buffers may be reused."""
         lr = self.current_lr
+        scale = 1.0 / (self.world * self.accum)
         ready = torch.cuda.Event()
         ready.record()
         with torch.cuda.stream(self.comm_stream):
             self.comm_stream.wait_event(ready)
-            if self.world > 1:
-                for b in flat_buffers:
-                    dist.all_reduce(b, op=dist.ReduceOp.SUM)
-            self._apply(params, lr, 1.0 / self.world)
+            if bucket is not None:
+                g = self._bucket_reduce(bucket, flat_grad)
+                self._bucket_update(bucket, g, lr, scale)
+            if small_params:
+                if self.world > 1:
+                    for t in small_bufs:
+                        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+                self._apply_small(small_params, lr, scale)
             done = torch.cuda.Event()
             done.record()
         return done
@@ -163,11 +332,8 @@ class TrainEngine:
         return cosine_lr(max(self.step_count - 1, 0), self.total_steps, self.lr, self.warmup_ratio)
 
     # -------------------------------------------------------------- one train step
-    def step(self, batch: dict) -> dict:
-        """batch: input_ids [B,L] (-200 at images), labels, attention_mask (host tensors), images
-        [N,3,S,S] (host, pinned, or device). Returns device scalars (no host sync here)."""
+    def _micro(self, batch: dict, first: bool, last: bool):
         m = self.model
-        self.step_count += 1
         dev = m.device
         images = batch["images"]
         if not images.is_cuda:
@@ -180,32 +346,76 @@ class TrainEngine:
             padded_positions = plan.batch * plan.seq_len
             plan = pack_plan(plan, self.pack_len)
             self.last_padding_saved = padded_positions - plan.batch * plan.seq_len
+        self.provider.accumulate = not first
+        self.provider.apply_now = last
         res, _ = self.hot.forward_backward(plan, images, self.provider, want_grad=True,
                                            n_save_gu=self.n_save_gu_layers,
-                                           train_embed=("model.embed_tokens.weight" in self.opt),
-                                           train_projector=("model.mm_projector.0.weight" in self.opt))
+                                           train_embed=("model.embed_tokens.weight" in self.opt or
+                                                        "model.embed_tokens.weight" in self.big_buckets),
+                                           train_projector=("model.mm_projector.0.weight" in self.small_state),
+                                           train_llm=self.train_llm,
+                                           train_lm_head=("lm_head.weight" in self.big_buckets or "lm_head.weight" in self.small_state),
+                                           train_vision_head=("vision_head.0.weight" in self.small_state))
+        return res, plan.batch * plan.seq_len
+
+    def step(self, batch) -> dict:
+        """batch: input_ids [B,L] (-200 at images), labels, attention_mask (host tensors), images [N,3,S,S] (host,
+        pinned, or device) — or, with gradient_accumulation_steps = k > 1, a list of k such micro-batches.
+        Returns device scalars (no host sync here); losses are the mean over the micro-batches, as HF logs them."""
+        micro = list(batch) if isinstance(batch, (list, tuple)) else [batch]
+        if len(micro) != self.accum:
+            raise ValueError(f"step() needs {self.accum} micro-batch(es) (gradient_accumulation_steps), got {len(micro)}")
+        self.step_count += 1
+        tot = None
+        tokens = 0
+        for i, mb in enumerate(micro):
+            res, n_tok = self._micro(mb, first=(i == 0), last=(i == len(micro) - 1))
+            tokens += n_tok
+            vals = torch.cat([res.loss.reshape(1), res.loss_language.reshape(1), res.loss_image_ar.reshape(1)])
+            tot = vals if tot is None else tot + vals
+        tot = tot / len(micro)
         if self.max_grad_norm is not None:
             self._clipped_update()
-        if self.comm_stream is not None:
-            torch.cuda.current_stream().wait_stream(self.comm_stream)
-        self.last_tokens = plan.batch * plan.seq_len
-        return dict(loss=res.loss, loss_language=res.loss_language, loss_image_ar=res.loss_image_ar,
-                    tokens=self.last_tokens)
+        torch.cuda.current_stream().wait_stream(self.comm_stream)
+        self.last_tokens = tokens
+        return dict(loss=tot[0], loss_language=tot[1:2], loss_image_ar=tot[2:3], tokens=tokens)
 
     def _clipped_update(self):
-        """Two-phase update with global-norm clipping (torch.nn.utils.clip_grad_norm_ semantics)."""
-        bufs = self.provider.buffers
-        sumsq = torch.zeros(1, dtype=torch.float32, device=self.model.device)
-        items = [(self.named_params[n], g) for n, g in bufs.items() if n in self.opt]
-        if self.world > 1:
-            for _, g in items:
-                dist.all_reduce(g, op=dist.ReduceOp.SUM)
-        inv = 1.0 / self.world
-        for _, g in items:
-            if g.dtype == torch.bfloat16 and g.numel() % 8 == 0:
-                ops.sumsq_accum(g.view(-1), sumsq)
-            else:
-                sumsq += g.float().pow(2).sum()
-        coef = ops.clip_coef(sumsq * (inv * inv), self.max_grad_norm)
-        self.last_grad_norm = coef[1:2]
-        self._apply(items, self.current_lr, inv, scale_tensor=coef[0:1])
+        """Two-phase update with global-norm clipping (torch.nn.utils.clip_grad_norm_ semantics on the averaged
+        gradient): reduce every bucket, sum the squared norms of the slices across ranks, then apply with the factor."""
+        pending, self.provider.pending = self.provider.pending, []
+        dev = self.model.device
+        lr = self.current_lr
+        inv = 1.0 / (self.world * self.accum)
+        ready = torch.cuda.Event()
+        ready.record()
+        with torch.cuda.stream(self.comm_stream):
+            self.comm_stream.wait_event(ready)
+            sq_sharded = torch.zeros(1, dtype=torch.float32, device=dev)
+            sq_repl = torch.zeros(1, dtype=torch.float32, device=dev)
+
+            def sumsq(t, acc):
+                if t.dtype == torch.bfloat16 and t.numel() % 8 == 0:
+                    ops.sumsq_accum(t.reshape(-1), acc)
+                else:
+                    acc += t.float().pow(2).sum()
+
+            slices = []
+            for bucket, flat, small, bufs in pending:
+                if bucket is not None:
+                    g = self._bucket_reduce(bucket, flat)
+                    sumsq(g, sq_sharded if self.shard_world > 1 else sq_repl)
+                    slices.append((bucket, g))
+                if self.world > 1:
+                    for t in bufs:
+                        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+                for t in bufs:
+                    sumsq(t, sq_repl)
+            if self.shard_world > 1:
+                dist.all_reduce(sq_sharded, op=dist.ReduceOp.SUM)
+            coef = ops.clip_coef((sq_sharded + sq_repl) * (inv * inv), self.max_grad_norm)
+            self.last_grad_norm = coef[1:2]
+            for bucket, g in slices:
+                self._bucket_update(bucket, g, lr, inv, scale_tensor=coef[0:1])
+            for _, _, small, _ in pending:
+                self._apply_small(small, lr, inv, scale_tensor=coef[0:1])

@@ -96,15 +96,18 @@ class MlpGelu(nn.Module):
         y = ops.gemm(a, self.fc2.weight, bias=self.fc2.bias, epilogue=ops.EPI_BIAS)
         return y, (x2, z, a)
 
-    def backward_train(self, saved, dy: torch.Tensor, grads: dict, need_dx: bool):
-        """grads: dict name -> tensor for '0.weight','0.bias','2.weight','2.bias' (bias fp32)."""
+    def backward_train(self, saved, dy: torch.Tensor, grads, need_dx: bool, accumulate: bool = False):
+        """grads: dict name -> tensor for '0.weight','0.bias','2.weight','2.bias' (bias fp32, zeroed by the caller unless
+        accumulating), or None when these parameters are frozen (only dx is produced)."""
         x2, z, a = saved
-        ops.gemm(dy, a, a_mn=True, b_mn=True, out=grads["2.weight"])
-        ops.colsum_accum(dy, grads["2.bias"])
+        if grads is not None:
+            ops.gemm(dy, a, a_mn=True, b_mn=True, out=grads["2.weight"], accumulate=accumulate)
+            ops.colsum_accum(dy, grads["2.bias"])
         da = ops.gemm(dy, self.fc2.weight, b_mn=True)
         dz = ops.gelu_bwd(z, da)
-        ops.gemm(dz, x2, a_mn=True, b_mn=True, out=grads["0.weight"])
-        ops.colsum_accum(dz, grads["0.bias"])
+        if grads is not None:
+            ops.gemm(dz, x2, a_mn=True, b_mn=True, out=grads["0.weight"], accumulate=accumulate)
+            ops.colsum_accum(dz, grads["0.bias"])
         if need_dx:
             return ops.gemm(dz, self.fc1.weight, b_mn=True)
         return None

@@ -217,10 +217,44 @@ class MetaMorphLlamaForCausalLM(nn.Module, MetaMorphMetaForCausalLM):
             for k in [k for k in sd if k.startswith(pre + "head.")]:
                 tower.vision_tower._extra_state_tensors[k[len(pre):]] = sd.pop(k)
             tower.vision_tower.invalidate_packed()
+        elif tower is not None:
+            # delay-loaded tower: keep the checkpoint's tower tensors for the coming load_model() instead of dropping
+            # them (a silently random frozen tower would poison every later step)
+            stash = {}
+            for k in [k for k in sd if k.startswith("model.vision_tower.")]:
+                v = sd.pop(k)
+                if k.startswith(pre):
+                    name = k[len(pre):]
+                    stash[name[len("vision_model."):] if name.startswith("vision_model.") else name] = v
+            if stash:
+                tower.stash_checkpoint_state(stash)
         else:
             for k in [k for k in sd if k.startswith("model.vision_tower.")]:
                 sd.pop(k)
         return super().load_state_dict(sd, strict=strict)
+
+    # names whose absence from a checkpoint is legitimate: the dead vision_proj layer, the tower's unused pooling head /
+    # post_layernorm, rotary buffers; projector / vision head / tower are absent from a plain LLaMA base checkpoint
+    # (stage 1 starts them from their initialisation, as HF `from_pretrained` does with a "newly initialized" warning)
+    _OPTIONAL_PREFIXES = ("model.vision_proj.", "model.vision_tower.", "model.mm_projector.", "vision_head.")
+
+    def check_loaded_keys(self, result, what: str):
+        """Inspect the IncompatibleKeys of a non-strict load: a LLaMA-core tensor (embeddings, decoder layers, final
+        norm, lm_head) that the checkpoint lacks means a naming mismatch that would leave random weights -> raise;
+        optional groups and unexpected keys are reported with a warning."""
+        import warnings
+        missing = list(result.missing_keys)
+        core = [k for k in missing if not k.startswith(self._OPTIONAL_PREFIXES)]
+        if core:
+            raise RuntimeError(f"{what}: {len(core)} core tensors are missing from the checkpoint (would stay randomly "
+                               f"initialised), e.g. {core[:4]}")
+        opt = sorted({k.split(".")[0] + "." + k.split(".")[1] for k in missing})
+        if opt:
+            warnings.warn(f"{what}: not in the checkpoint, left at their initialisation: {opt}", stacklevel=2)
+        unexpected = [k for k in result.unexpected_keys if "rotary_emb.inv_freq" not in k]
+        if unexpected:
+            warnings.warn(f"{what}: {len(unexpected)} unexpected tensors ignored, e.g. {unexpected[:4]}", stacklevel=2)
+        return result
 
     def save_pretrained(self, save_directory: str, state_dict=None, max_shard_size="5GB", safe_serialization=True,
                         **kwargs):
@@ -246,22 +280,19 @@ class MetaMorphLlamaForCausalLM(nn.Module, MetaMorphMetaForCausalLM):
             config = MetaMorphConfig(**raw)
         ctor = {k: kwargs.pop(k) for k in ("use_vision_ar", "vision_coef", "vision_head", "normalize_vision",
                                            "apply_softmax", "vision_delay_load", "full_ar") if k in kwargs}
+        # the tower is built AFTER the checkpoint has been read, so that its tensors (model.vision_tower.vision_tower.*)
+        # are the first source of its weights; only then the pretrained SigLIP (siglip_tower.SiglipVisionTower.load_model)
+        load_tower_now = not ctor.get("vision_delay_load", True)
+        ctor["vision_delay_load"] = True
         model = cls(config, dtype=torch_dtype, device=device, **ctor)
+        from .. import checkpoint
+        sd = checkpoint.load_model_state(path)     # index-aware; never reads optimizer-*.safetensors of a checkpoint-N dir
+        if not sd:
+            raise FileNotFoundError(f"no model weights (*.safetensors / pytorch_model*.bin) under {path}")
+        model.check_loaded_keys(model.load_state_dict(sd, strict=False), f"from_pretrained({path})")
         tower = model.get_vision_tower()
-        if tower is not None and not tower.is_loaded and not ctor.get("vision_delay_load", True):
+        if load_tower_now and tower is not None and not tower.is_loaded:
             tower.load_model(device=device, dtype=torch_dtype)
-        files = sorted(f for f in os.listdir(path) if f.endswith(".safetensors") or
-                       (f.startswith("pytorch_model") and f.endswith(".bin")))
-        sd = {}
-        for f in files:
-            fp = os.path.join(path, f)
-            if f.endswith(".safetensors"):
-                from safetensors.torch import load_file
-                sd.update(load_file(fp))
-            else:
-                sd.update(torch.load(fp, map_location="cpu"))
-        if sd:
-            model.load_state_dict(sd, strict=False)
         return model
 
     # ------------------------------------------------------------------ gradients for loss.backward()

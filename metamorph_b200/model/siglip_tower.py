@@ -198,27 +198,93 @@ class SiglipVisionTower(nn.Module):
         self._tower_dims = dict(tower_dims or getattr(args, "mm_vision_tower_dims", None) or {})
         self.hidden_size = VISION_FEATURE_DIM
         self.image_processor = None
+        self._pending_state = None
+        self._tower_path = getattr(args, "mm_vision_tower_path", None)
+        self._allow_random_init = bool(getattr(args, "mm_vision_tower_random_init", False))
         if not delay_load:
             self.load_model()
 
-    def load_model(self, device_map=None, state_dict=None, device=None, dtype=torch.bfloat16):
-        """Builds the tower. The reference downloads google/siglip-so400m-patch14-384
-        (siglip_encoder.py:113); offline, weights come from the checkpoint's
-        `model.vision_tower.vision_tower.*` keys (or stay randomly initialised)."""
+    HF_TOWER_NAME = "google/siglip-so400m-patch14-384"   # what the reference downloads (siglip_encoder.py:113)
+
+    def stash_checkpoint_state(self, state_dict):
+        """Tower tensors found in a model checkpoint while the tower is still delay-loaded: kept (host side) and applied
+        by the next load_model() instead of being dropped."""
+        self._pending_state = dict(state_dict)
+
+    def _pretrained_state(self):
+        """SigLIP weights as the reference gets them: `AutoModel.from_pretrained("google/siglip-so400m-patch14-384")
+        .vision_model` (siglip_encoder.py:113,122). A local directory can be named with MM_SIGLIP_PATH or
+        config.mm_vision_tower_path; offline, the hub cache is the only other source. None if nothing is available."""
+        import os
+        src = os.environ.get("MM_SIGLIP_PATH") or self._tower_path or self.HF_TOWER_NAME
+        try:
+            from transformers import SiglipVisionModel
+            hf = SiglipVisionModel.from_pretrained(src)
+        except Exception as e:  # noqa: BLE001 - no network / no cache / not a SigLIP directory
+            self._pretrained_error = f"{type(e).__name__}: {str(e).splitlines()[0][:200]}"
+            return None
+        return {k[len("vision_model."):]: v for k, v in hf.state_dict().items() if k.startswith("vision_model.")}
+
+    def load_model(self, device_map=None, state_dict=None, device=None, dtype=torch.bfloat16, allow_random_init=None):
+        """Builds the tower and loads its weights. Sources, in order: the `state_dict` argument; tower tensors of the
+        model checkpoint that was loaded while the tower was delay-loaded (`model.vision_tower.vision_tower.*`); the
+        pretrained SigLIP the reference downloads (siglip_encoder.py:113). With none of them the call RAISES — a
+        silently random frozen tower would make every training run regress against noise — unless random init was
+        asked for explicitly (`allow_random_init=True` / `config.mm_vision_tower_random_init`: synthetic benchmarks
+        and tests, which then load their own tower tensors through `model.load_state_dict`)."""
         self.vision_model = "siglip"
         dims = dict(width=1152, inter=4304, n_layers=27, n_heads=16, image_size=self._image_size, patch=14)
         dims.update(self._tower_dims)
         self.vision_tower = SiglipVisionTransformerParams(dtype=dtype, device=device, **dims)
-        if state_dict is not None:
-            self.vision_tower.load_state_dict(state_dict, strict=False)
-        try:  # image processor is host-side plumbing; only available when HF assets are cached
-            from transformers import SiglipImageProcessor
-            self.image_processor = SiglipImageProcessor(size={"height": 384, "width": 384})
-            self.image_processor.crop_size = {"height": 384, "width": 384}
-        except Exception:  # noqa: BLE001
-            self.image_processor = None
+        sd, source = state_dict, "state_dict argument"
+        if sd is None and self._pending_state is not None:
+            sd, source = self._pending_state, "model checkpoint"
+        if sd is None:
+            sd, source = self._pretrained_state(), "pretrained SigLIP"
+        if allow_random_init is None:
+            allow_random_init = self._allow_random_init
+        if sd is not None:
+            own = set(self.vision_tower.state_dict().keys())
+            res = self.vision_tower.load_state_dict({k: v for k, v in sd.items() if k in own}, strict=False)
+            missing = [k for k in res.missing_keys if not k.startswith(("post_layernorm.", "head."))]
+            if missing:
+                raise RuntimeError(f"SigLIP tower weights from the {source} lack {len(missing)} tensors, e.g. {missing[:4]}")
+            for k, v in sd.items():
+                if k.startswith("head."):
+                    self.vision_tower._extra_state_tensors[k] = v
+            self.vision_tower.invalidate_packed()
+            self.weights_source = source
+        elif allow_random_init:
+            import warnings
+            warnings.warn("SiglipVisionTower: RANDOMLY INITIALISED tower (allow_random_init) - valid for synthetic "
+                          "benchmarks/tests only", stacklevel=2)
+            self.weights_source = "random init"
+        else:
+            raise RuntimeError(
+                "SiglipVisionTower.load_model: no SigLIP weights available - the checkpoint holds no "
+                "model.vision_tower.vision_tower.* tensors and the pretrained tower could not be loaded "
+                f"({getattr(self, '_pretrained_error', 'unknown')}). Point MM_SIGLIP_PATH / config.mm_vision_tower_path at a "
+                f"local copy of {self.HF_TOWER_NAME}, or pass allow_random_init=True for synthetic runs.")
+        self._pending_state = None
+        self.image_processor = self._make_image_processor(device)
         self.hidden_size = self.vision_tower.cfg.hidden_size
         self.is_loaded = True
+
+    def _make_image_processor(self, device):
+        """on a CUDA device the drop-in caller gets the on-GPU pre-processing (bit-exact with the
+        HF PIL processor, tests/test_preprocess_gpu.py) behind the same `.preprocess(images, return_tensors)` call; the
+        HF CPU processor only when the tower lives on the host (CPU-side plumbing tests)."""
+        dev = torch.device(device) if device is not None else self.vision_tower.device
+        if dev.type == "cuda":
+            from ..preprocess import SiglipGpuImageProcessor
+            return SiglipGpuImageProcessor(device=dev)
+        try:
+            from transformers import SiglipImageProcessor
+            proc = SiglipImageProcessor(size={"height": 384, "width": 384})
+            proc.crop_size = {"height": 384, "width": 384}
+            return proc
+        except Exception:  # noqa: BLE001
+            return None
 
     def _n_layers_to_run(self) -> int:
         L = self.vision_tower.cfg.num_hidden_layers

@@ -317,7 +317,7 @@ def attn_bwd(q, k, v, o, dout, lse, dq, dk, dv, B, T, Hq, Hkv, head_dim, scale, 
     need = fn(c_int(B), c_int(T), c_int(Hq))
     if workspace is None or workspace.numel() < need:
         workspace = torch.empty(need, dtype=torch.uint8, device=q.device)
-    use_tc = (ATTN_BWD_TC and T % 4 == 0) if tc is None else tc   # tc path bulk-loads 16B-aligned stat rows
+    use_tc = ATTN_BWD_TC if tc is None else tc   # tc=False: the mma.sync kernel, kept as a test-only comparison
     call("mm_attn_bwd_tc" if use_tc else "mm_attn_bwd", ptr(q), ptr(k), ptr(v), ptr(o), ptr(dout), ptr(lse), ptr(dq), ptr(dk), ptr(dv),
          ptr(seqlens), ll(q.stride(0)), ll(k.stride(0)), ll(v.stride(0)), ll(o.stride(0)),
          ll(dout.stride(0)), ll(dq.stride(0)), ll(dk.stride(0)), ll(dv.stride(0)), c_int(B), c_int(T),

@@ -33,6 +33,7 @@ def make_config(llama: dict = None, siglip: dict = None, num_image_tokens: int =
     s = dict(SIGLIP_SO400M)
     s.update(siglip or {})
     c.mm_vision_tower_dims = s
+    c.mm_vision_tower_random_init = True    # synthetic configs never have pretrained SigLIP weights
     return c
 
 
@@ -41,7 +42,7 @@ def build_model(config, device="cuda"):
     from .model import MetaMorphLlamaForCausalLM
     model = MetaMorphLlamaForCausalLM(config, vision_head="mlp", normalize_vision=True, vision_delay_load=True,
                                       device=device)
-    model.get_vision_tower().load_model(device=device)
+    model.get_vision_tower().load_model(device=device, allow_random_init=True)   # synthetic: random-init tower
     for p in model.get_vision_tower().parameters():
         p.requires_grad = False
     return model

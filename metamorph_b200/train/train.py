@@ -121,11 +121,20 @@ def train(attn_implementation=None, data_module_factory: Optional[Callable[..., 
                                           vision_coef=model_args.vision_coef, vision_head=model_args.vision_head_type,
                                           normalize_vision=model_args.normalize_vision, device=dev)
     model.config.use_cache = False
-    if model_args.vision_tower is not None and model.get_vision_tower() is None:
+    if model_args.vision_tower is not None and model_args.vision_tower != "None":
+        # train.py:1498-1502: always (re-)initialise the vision modules from model_args — this is also what loads a
+        # stage-1 `--pretrain_mm_mlp_adapter` (metamorph_arch.py:91-96), whether or not the config already names a tower
         model.get_model().initialize_vision_modules(model_args=model_args)
     tower = model.get_vision_tower()
     if tower is not None and not tower.is_loaded:
-        tower.load_model(device=dev)
+        tower.load_model(device=dev)          # checkpoint tensors > pretrained SigLIP > (synthetic configs only) random
+    from ..constants import IMAGE_END_TOKEN_ID
+    if model_args.mm_use_im_start_end and model.config.vocab_size <= IMAGE_END_TOKEN_ID:
+        # the reference grows the vocabulary by <image_start>/<image_end> through initialize_vision_tokenizer
+        # (train.py:1545, needs the tokenizer); without a tokenizer the checkpoint must already contain both rows
+        raise ValueError(f"vocab_size {model.config.vocab_size} has no rows for <image_start>/<image_end> "
+                         f"({IMAGE_END_TOKEN_ID - 1}, {IMAGE_END_TOKEN_ID}): run initialize_vision_tokenizer(model_args, tokenizer) "
+                         "on the model first")
     for k in ("mm_use_im_start_end", "mm_use_im_patch_token", "num_image_tokens", "image_token_reduction",
               "normalize_vision", "freeze_vision", "vision_coef", "vision_head_type"):
         setattr(model.config, k, getattr(model_args, k))
@@ -159,10 +168,15 @@ def train(attn_implementation=None, data_module_factory: Optional[Callable[..., 
     if resume is not None:                                    # train.py:1592-1595: checkpoint-* present -> resume
         start = checkpoint.load_training_checkpoint(engine, resume)
         rank0_print(f"resumed from {resume} at step {start}")
-        for _ in range(start):                                # keep the data stream aligned with the step counter
+        for _ in range(start * accum):                        # keep the data stream aligned with the step counter
             next(batches)
+    elif training_args.output_dir and os.path.isdir(training_args.output_dir) and any(
+            d.startswith("checkpoint-") for d in os.listdir(training_args.output_dir)):
+        rank0_print(f"{training_args.output_dir} holds checkpoint-* folders without trainer_state.json (stage-1 projector "
+                    "artefacts are not resumable): starting from step 0")
     for step in range(start, training_args.max_steps):
-        out = engine.step(next(batches))
+        # one optimizer step = `gradient_accumulation_steps` micro-batches of per_device_train_batch_size samples
+        out = engine.step([next(batches) for _ in range(accum)] if accum > 1 else next(batches))
         if (step + 1) % training_args.logging_steps == 0:
             vals = torch.cat([out["loss"].reshape(1), out["loss_language"].reshape(1), out["loss_image_ar"].reshape(1)])
             if world > 1:
@@ -171,14 +185,16 @@ def train(attn_implementation=None, data_module_factory: Optional[Callable[..., 
             l, ll_, li = vals.tolist()
             model.loss_language, model.loss_image_ar = ll_, li
             rank0_print(f"step {step + 1}: loss {l:.4f} loss_language {ll_:.4f} loss_image_ar {li:.4f} lr {engine.current_lr:.3e}")
-        if training_args.save_steps > 0 and (step + 1) % training_args.save_steps == 0 and rank == 0 \
-                and training_args.output_dir:
+        if training_args.save_steps > 0 and (step + 1) % training_args.save_steps == 0 and training_args.output_dir:
             torch.cuda.synchronize()
             if model_args.tune_mm_mlp_adapter:                # metamorph_trainer.py:273-291
-                checkpoint.save_mm_projector_checkpoint(model, training_args.output_dir, step + 1,
-                                                        use_im_start_end=model_args.mm_use_im_start_end)
-            else:
+                if rank == 0:
+                    checkpoint.save_mm_projector_checkpoint(model, training_args.output_dir, step + 1,
+                                                            use_im_start_end=model_args.mm_use_im_start_end)
+            else:                                             # every rank: the optimizer state is sharded over ranks
                 checkpoint.save_training_checkpoint(engine, training_args.output_dir)
+            if world > 1:
+                dist.barrier()
     if rank == 0 and training_args.output_dir:
         torch.cuda.synchronize()
         if model_args.tune_mm_mlp_adapter:                    # safe_save_model_for_hf_trainer, train.py:189-207

@@ -13,58 +13,13 @@ import sys
 
 import torch
 
-os.environ.setdefault("WANDB_MODE", "disabled")
-os.environ.setdefault("TRANSFORMERS_OFFLINE", "1")
-sys.dont_write_bytecode = True
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
-sys.path.insert(0, "/root/reference")   # first: `metamorph` must be the reference, not this repo's alias package
 
+from oracle.ref_model import activate, build_reference, pin_decode_mask_semantics  # noqa: E402
 from oracle.weights import TINY, make_batch, make_weights  # noqa: E402
 
-
-def build_reference(cfg, weights, dtype=torch.float32, num_image_tokens=None, max_len=None):
-    from metamorph.model import MetaMorphLlamaForCausalLM
-    from metamorph.model.language_model.metamorph_llama import MetaMorphConfig
-    from transformers import SiglipVisionConfig, SiglipVisionModel
-    c = MetaMorphConfig(hidden_size=cfg["hidden"], intermediate_size=cfg["inter"],
-                        num_hidden_layers=cfg["layers"], num_attention_heads=cfg["heads"],
-                        num_key_value_heads=cfg["kv_heads"], head_dim=cfg["head_dim"], vocab_size=cfg["vocab"],
-                        rms_norm_eps=cfg["rms_eps"], rope_theta=cfg["rope_theta"],
-                        max_position_embeddings=8192, attention_bias=False, tie_word_embeddings=False)
-    c.mm_vision_tower = "siglip/CLIP-ViT-SO400M-14-384"
-    c.mm_projector_type = "mlp2x_gelu"
-    c.mm_hidden_size = 1152
-    c.num_image_tokens = num_image_tokens or cfg["image_tokens"]
-    c.image_token_reduction = "interpolation"
-    c.normalize_vision = True
-    c.freeze_vision = True
-    c.vision_head_type = "mlp"
-    c.mm_vision_select_layer = -1
-    c.tokenizer_model_max_length = max_len or cfg["max_len"]
-    c.tokenizer_padding_side = "right"
-    c._attn_implementation = "eager"
-    model = MetaMorphLlamaForCausalLM(c, vision_head="mlp", normalize_vision=True)
-    vt = model.get_vision_tower()
-    vt.vision_tower = SiglipVisionModel(SiglipVisionConfig(
-        hidden_size=cfg["siglip_width"], intermediate_size=cfg["siglip_inter"],
-        num_hidden_layers=cfg["siglip_layers"], num_attention_heads=cfg["siglip_heads"],
-        image_size=cfg["image_size"], patch_size=14))
-    vt.is_loaded = True
-    sd = {}
-    tp = "model.vision_tower.vision_tower."
-    for k, v in weights.items():
-        if k.startswith(tp):
-            sd[tp + "vision_model." + k[len(tp):]] = v
-        else:
-            sd[k] = v
-    missing, unexpected = model.load_state_dict(sd, strict=False)
-    missing = [m for m in missing if ".head." not in m and "rotary" not in m]
-    assert not unexpected, unexpected
-    assert not missing, missing
-    model = model.to(dtype)
-    model.eval()
-    return model
+activate("/root/reference")   # first on sys.path: `metamorph` must be the reference, not this repo's alias package
 
 
 def run_forward_case(model, ids, mask, labs, images, with_grads):
@@ -174,19 +129,7 @@ def main():
 
     # ---------------- case 4: greedy decode (no cache) of the reference, 4 visual tokens per image
     ref_dec = build_reference(cfg, W, torch.float32, num_image_tokens=4)
-    # Version-drift shim: greedy_decode passes a [1,1] all-ones attention_mask together
-    # with the full-length inputs_embeds (metamorph_llama.py:524). Under the pinned transformers 4.45
-    # that mask is a no-op (pure causal attention); transformers 5.x broadcasts it into a different
-    # mask. Drop it so the golden vectors carry the pinned-version semantics.
-    _orig_llm_forward = ref_dec.llm_forward
-
-    def _llm_forward_445(*a, **kw):
-        am = kw.get("attention_mask")
-        if am is not None and am.shape[-1] == 1 and kw["inputs_embeds"].shape[1] != 1:
-            kw["attention_mask"] = None
-        return _orig_llm_forward(*a, **kw)
-
-    ref_dec.llm_forward = _llm_forward_445
+    pin_decode_mask_semantics(ref_dec)   # transformers 4.45 semantics of the [1,1] mask (oracle/ref_model.py)
     prompt = torch.tensor([[128000] + torch.randint(0, 128000, (11,), generator=rng).tolist()])
     with torch.no_grad():
         first = ref_dec.generate(prompt, max_new_tokens=0)[0]

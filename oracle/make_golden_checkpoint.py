@@ -9,11 +9,12 @@ that the real reference (`model.vision_model`, siglip_encoder.py:122) does not h
 import json
 import os
 
-from oracle.make_golden import build_reference
+from oracle.ref_model import activate, build_reference
 from oracle.weights import TINY, make_weights
 
 
 def main():
+    activate("/root/reference")
     model = build_reference(TINY, make_weights(TINY))
     tp = "model.vision_tower.vision_tower."
     out = {}

@@ -251,8 +251,10 @@ def full_forward(p, cfg, input_ids, attention_mask, labels, images):
 
 @torch.no_grad()
 def greedy_decode_nocache(p, cfg, inputs_embeds: torch.Tensor, max_new_tokens: int, start_id=128256,
-                          end_id=128257, eos=(128001, 128009)):
-    """metamorph_llama.py:502-597: re-runs the whole growing prefix every step (batch 1)."""
+                          end_id=128257, eos=(128001, 128009), trace=None):
+    """metamorph_llama.py:502-597: re-runs the whole growing prefix every step (batch 1).
+    `trace` (a list) receives one dict per step: argmax token, top-1 minus top-2 logit, and the mode flags BEFORE the
+    step's state update (used by oracle/make_golden_decode_quirks.py to pick cases with a safe logit margin)."""
     x = inputs_embeds.float()
     ids, imgs = [], []
     in_image, n_img_tok, n_out = False, 0, 0
@@ -266,7 +268,11 @@ def greedy_decode_nocache(p, cfg, inputs_embeds: torch.Tensor, max_new_tokens: i
             pred_z = F.normalize(mlp_gelu(p, "vision_head.", hidden[:, -1]), p=2, dim=-1)
             hidden = hidden.clone()
             hidden[:, -1] = mlp_gelu(p, "model.mm_projector.", pred_z)
-        tok = int(F.linear(hidden[:, -1], p["lm_head.weight"].float()).argmax(-1))
+        logits = F.linear(hidden[:, -1], p["lm_head.weight"].float())
+        tok = int(logits.argmax(-1))
+        if trace is not None:
+            top2 = logits[0].topk(2).values
+            trace.append(dict(tok=tok, margin=float(top2[0] - top2[1]), in_image=in_image, n_img_tok=n_img_tok))
         emb = p["model.embed_tokens.weight"].float()[tok][None, None]
         if not in_image and tok == start_id:
             in_image = True; ids.append(tok); x = torch.cat([x, emb], 1)

@@ -32,7 +32,7 @@ def build_product_model(cfg, weights, device="cuda", **kw):
     c = product_config(cfg, **kw)
     model = MetaMorphLlamaForCausalLM(c, vision_head="mlp", normalize_vision=True, vision_delay_load=True,
                                       device=device)
-    model.get_vision_tower().load_model(device=device)
+    model.get_vision_tower().load_model(device=device, allow_random_init=True)   # tower tensors follow via load_state_dict
     missing, unexpected = model.load_state_dict({k: v.to(torch.bfloat16) for k, v in weights.items()}, strict=False)
     assert not unexpected, unexpected
     assert not missing, missing

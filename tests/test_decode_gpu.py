@@ -252,3 +252,31 @@ def test_continuous_batching_matches_single_request_decodes(cuda_device):
     ids_f, img_f = results[free_rid]
     assert 1 <= ids_f.numel() + img_f.shape[0] <= 6
     assert results[rids[3]][0].cpu().tolist()[-1] == 128009 and results[rids[3]][0].numel() == 4
+
+
+@pytest.mark.parametrize("quirk", ["q1", "q2"])
+def test_served_request_matches_reference_golden(cuda_device, quirk):
+    """SURVEY section 8f N4 pinned to the REFERENCE (not to the product's own greedy_decode): a request served by the
+    continuous batcher next to an unrelated one must reproduce, free-running, the token ids and visual embeddings of the
+    reference's generate() stored by oracle/make_golden_decode_quirks.py."""
+    import os
+    from metamorph_b200.engine.serve import ContinuousBatcher
+    from oracle.weights import TINY, make_weights, with_sparse_lm_head
+    from tests.helpers import build_product_model
+    d = torch.load(os.path.join(os.path.dirname(__file__), "golden", "greedy_decode_quirks.pt"), weights_only=False)[quirk]
+    model = build_product_model(TINY, with_sparse_lm_head(make_weights(TINY), d["live_rows"])[0],
+                                num_image_tokens=d["num_image_tokens"])
+    model.eval()
+    srv = ContinuousBatcher(model, max_slots=2, max_context=64, max_new_tokens=24, poll_every=3,
+                            start_image_token_id=d["start_image_token_id"], end_image_token_id=d["end_image_token_id"],
+                            eos_token_id=list(d["eos_token_id"]))
+    g = torch.Generator().manual_seed(5)
+    other = model.get_model().embed_tokens(torch.randint(0, 128000, (1, 9), generator=g).cuda())
+    rid_other = srv.submit(other, max_new_tokens=20)
+    rid = srv.submit(model.get_model().embed_tokens(d["prompt"].cuda()), max_new_tokens=d["max_new_tokens"])
+    results = {r: payload for r, kind, payload in srv.run() if kind == "done"}
+    assert set(results) == {rid, rid_other}
+    ids, img = results[rid]
+    assert ids.cpu().tolist() == [int(t) for t in d["ids"]]
+    assert tuple(img.shape) == tuple(d["image_embeds"].shape)
+    torch.testing.assert_close(img.float().cpu(), d["image_embeds"], rtol=0, atol=1e-2)

@@ -147,6 +147,32 @@ def test_decode_kv_cache_matches_reference_nocache(cuda_device, weights):
     assert ids2[0].cpu().tolist() == [int(t) for t in ref_ids]
 
 
+@pytest.mark.parametrize("quirk", ["q1", "q2"])
+def test_decode_free_running_reference_quirks(cuda_device, weights, quirk):
+    """FREE-RUNNING (no teacher forcing) token-exactness against the reference's own generate() on prompts whose every
+    step has a top-1/top-2 logit margin far above bf16 noise (oracle/make_golden_decode_quirks.py), covering the two
+    state-machine quirks of metamorph_llama.py:502-597: q1 = EOS raised by the overwritten hidden state in the middle of
+    an image (fewer than num_image_tokens embeddings come back); q2 = a second <image_start> before any <image_end>
+    (tokens keep being appended as text while every step runs the decoding branch)."""
+    allq = torch.load(os.path.join(G, "greedy_decode_quirks.pt"), weights_only=False)
+    d = allq[quirk]
+    from oracle.weights import with_sparse_lm_head
+    model = build_product_model(TINY, with_sparse_lm_head(weights, d["live_rows"])[0], num_image_tokens=d["num_image_tokens"])
+    model.eval()
+    ids, img = model.generate(d["prompt"].cuda(), output_image=True, max_new_tokens=d["max_new_tokens"],
+                              start_image_token_id=d["start_image_token_id"],
+                              end_image_token_id=d["end_image_token_id"], eos_token_id=list(d["eos_token_id"]))
+    assert ids[0].cpu().tolist() == [int(t) for t in d["ids"]], (quirk, ids[0].cpu().tolist(), d["ids"].tolist(), d["min_margin"])
+    assert tuple(img.shape) == tuple(d["image_embeds"].shape)
+    if quirk == "q1":
+        assert img.shape[0] < d["num_image_tokens"]                  # generation ended inside the image
+    else:
+        modes = [m for _, m, _ in d["trace"]]
+        assert any(modes[k] and d["trace"][k][2] == d["num_image_tokens"] for k in range(len(modes)))   # stuck-in-image state reached
+    # unit-norm embeddings: 1e-2 absolute = the bf16 budget of a 2-layer path (north star: 1e-3 relative on logits)
+    torch.testing.assert_close(img.float().cpu(), d["image_embeds"], rtol=0, atol=1e-2)
+
+
 def test_missing_library_or_cpu_tensor_fails_loudly(model):
     from metamorph_b200._lib import MetaMorphB200Error
     from metamorph_b200 import ops

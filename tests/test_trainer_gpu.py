@@ -131,6 +131,13 @@ def test_packed_step_equals_padded_step(cuda_device):
     out_a, out_b = e_a.step(_batch()), e_b.step(_batch())
     torch.cuda.synchronize()
     assert e_b.last_padding_saved > 0 and out_b["tokens"] < out_a["tokens"]
+    # ... and, directly, the REFERENCE's losses on this batch (tests/golden/forward_backward_tiny.pt, made by the reference's
+    # own forward): the packed layout is held to the reference, not only to the product's padded layout
+    import os
+    fb = torch.load(os.path.join(os.path.dirname(__file__), "golden", "forward_backward_tiny.pt"), weights_only=False)
+    for k in ("loss", "loss_language", "loss_image_ar"):
+        ref, got = float(fb[k]), float(out_b[k])
+        assert abs(got - ref) <= 1e-3 * abs(ref) + 2e-3, ("packed vs reference", k, got, ref)
     for k in ("loss", "loss_language", "loss_image_ar"):
         a, b = float(out_a[k]), float(out_b[k])
         assert abs(a - b) <= 1e-3 * abs(a) + 1e-4, (k, a, b)
