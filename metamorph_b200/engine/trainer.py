@@ -113,6 +113,27 @@ class ShardedBucket:
         return views
 
 
+def bucket_reduce(b: ShardedBucket, flat_grad: torch.Tensor, world: int) -> torch.Tensor:
+    """This rank's slice of the gradient SUM over ranks (the whole buffer when the state is not sharded)."""
+    if world == 1:
+        return flat_grad
+    if b.world == 1:                                   # replicated state: plain all-reduce
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
+        return flat_grad
+    dist.reduce_scatter_tensor(b.gshard, flat_grad, op=dist.ReduceOp.SUM)
+    return b.gshard
+
+
+def bucket_update(b: ShardedBucket, gslice: torch.Tensor, adamw) -> None:
+    """`adamw(p16_out, p32, m, v, grad)` on this rank's slice; the updated bf16 slice then reaches every rank's flat
+    parameter buffer through the all-gather."""
+    if b.world == 1:
+        adamw(b.flat, b.p32, b.m, b.v, gslice)
+        return
+    adamw(b.pshard, b.p32, b.m, b.v, gslice)
+    dist.all_gather_into_tensor(b.flat, b.pshard)
+
+
 class BucketGradProvider(GradProvider):
     """Hands the hot path its gradient destinations and fires a bucket's collective + AdamW as soon as it is complete.
 
@@ -286,21 +307,11 @@ class TrainEngine:
 
     def _bucket_reduce(self, b: ShardedBucket, flat_grad: torch.Tensor) -> torch.Tensor:
         """(comm stream) -> this rank's slice of the summed gradient."""
-        if self.world == 1:
-            return flat_grad
-        if self.shard_world == 1:
-            dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
-            return flat_grad
-        dist.reduce_scatter_tensor(b.gshard, flat_grad, op=dist.ReduceOp.SUM)
-        return b.gshard
+        return bucket_reduce(b, flat_grad, self.world)
 
     def _bucket_update(self, b: ShardedBucket, gslice, lr, grad_scale, scale_tensor=None):
         """(comm stream) fused AdamW on the slice, then the updated bf16 slice goes back into every rank's flat buffer."""
-        if self.shard_world == 1:
-            self._adamw(b.flat, b.p32, b.m, b.v, gslice, lr, grad_scale, scale_tensor)
-            return
-        self._adamw(b.pshard, b.p32, b.m, b.v, gslice, lr, grad_scale, scale_tensor)
-        dist.all_gather_into_tensor(b.flat, b.pshard)
+        bucket_update(b, gslice, lambda p16, p32, m, v, g: self._adamw(p16, p32, m, v, g, lr, grad_scale, scale_tensor))
 
     def reduce_and_apply(self, bucket: Optional[ShardedBucket], flat_grad, small_params, small_bufs):
         """Collective + AdamW of one completed bucket (and/or of small replicated tensors) on the side stream.

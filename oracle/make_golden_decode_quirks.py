@@ -34,7 +34,7 @@ from oracle.weights import TINY, make_weights, with_sparse_lm_head  # noqa: E402
 
 NTOK = 4
 MAXNEW = 12
-MIN_MARGIN = 0.03
+MIN_MARGIN = 0.08      # (top1 - top2) / max|logit| at EVERY step; bf16 noise is ~0.5 % of the logit scale
 LIVE_ROWS = 16
 
 
@@ -56,7 +56,7 @@ def search(W, cfg):
             if s in [t["tok"] for t in tr0[:i]]:
                 continue
             ids, imgs, tr = decode(W, cfg, prompt, s, ())
-            margin = min(t["margin"] for t in tr)
+            margin = min(t["margin"] / t["scale"] for t in tr)
             if margin < MIN_MARGIN:
                 continue
             # Q2: s re-emitted after the image block with n_img_tok == NTOK, at least 3 more steps follow
@@ -94,8 +94,8 @@ def main():
         assert float((img_r.float() - imgs_o).abs().max()) < 1e-4
         out[name] = dict(prompt=c["prompt"], start_image_token_id=c["start"], end_image_token_id=-1, eos_token_id=list(c["eos"]),
                          max_new_tokens=MAXNEW, num_image_tokens=NTOK, live_rows=LIVE_ROWS, ids=ids_r[0].clone(), image_embeds=img_r.float().clone(),
-                         min_margin=min(t["margin"] for t in tr), trace=[(t["tok"], t["in_image"], t["n_img_tok"]) for t in tr])
-        print(name, "ids", ids_r[0].tolist(), "embeds", tuple(img_r.shape), "min margin %.4f" % out[name]["min_margin"],
+                         min_margin=min(t["margin"] / t["scale"] for t in tr), trace=[(t["tok"], t["in_image"], t["n_img_tok"]) for t in tr])
+        print(name, "ids", ids_r[0].tolist(), "embeds", tuple(img_r.shape), "min relative margin %.4f" % out[name]["min_margin"],
               [(t["tok"], int(t["in_image"]), t["n_img_tok"]) for t in tr])
     torch.save(out, os.path.join(REPO, "tests", "golden", "greedy_decode_quirks.pt"))
 

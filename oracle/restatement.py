@@ -253,7 +253,8 @@ def full_forward(p, cfg, input_ids, attention_mask, labels, images):
 def greedy_decode_nocache(p, cfg, inputs_embeds: torch.Tensor, max_new_tokens: int, start_id=128256,
                           end_id=128257, eos=(128001, 128009), trace=None):
     """metamorph_llama.py:502-597: re-runs the whole growing prefix every step (batch 1).
-    `trace` (a list) receives one dict per step: argmax token, top-1 minus top-2 logit, and the mode flags BEFORE the
+    `trace` (a list) receives one dict per step: argmax token, top-1 minus top-2 logit, the largest |logit| (the
+    scale bf16 noise is relative to: image-mode steps see the small projector output), and the mode flags BEFORE the
     step's state update (used by oracle/make_golden_decode_quirks.py to pick cases with a safe logit margin)."""
     x = inputs_embeds.float()
     ids, imgs = [], []
@@ -272,7 +273,8 @@ def greedy_decode_nocache(p, cfg, inputs_embeds: torch.Tensor, max_new_tokens: i
         tok = int(logits.argmax(-1))
         if trace is not None:
             top2 = logits[0].topk(2).values
-            trace.append(dict(tok=tok, margin=float(top2[0] - top2[1]), in_image=in_image, n_img_tok=n_img_tok))
+            trace.append(dict(tok=tok, margin=float(top2[0] - top2[1]), scale=float(logits[0].abs().max()),
+                              in_image=in_image, n_img_tok=n_img_tok))
         emb = p["model.embed_tokens.weight"].float()[tok][None, None]
         if not in_image and tok == start_id:
             in_image = True; ids.append(tok); x = torch.cat([x, emb], 1)
