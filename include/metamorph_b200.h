@@ -98,7 +98,11 @@ int mm_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse
                 long long ldq, long long ldk, long long ldv, long long ldo, int B, int T, int Hq, int Hkv,
                 int head_dim, int causal, float scale, cudaStream_t s);
 long long mm_attn_bwd_workspace_bytes(int B, int T, int Hq);
-/* tcgen05 / TMEM / TMA flash attention for head_dim 128 (csrc/attention_tc.cu); same contracts as above. */
+/* tcgen05 / TMEM / TMA flash attention for head_dim 128 (csrc/attention_tc.cu forward, csrc/attention_bwd_tc.cu backward:
+ * a query-stationary dQ kernel + a key-stationary dK/dV kernel, no atomics -> bit-reproducible); same contracts as above.
+ * Rows >= seqlens[b] are outside the sequence: zero dQ/dK/dV, their dO is ignored. Backward workspace: lse*log2e and
+ * delta, mm_attn_bwd_tc_workspace_bytes. */
+long long mm_attn_bwd_tc_workspace_bytes(int B, int T, int Hq);
 int mm_attn_fwd_tc(const void* q, const void* k, const void* v, void* o, float* lse, const int* seqlens,
                    long long ldq, long long ldk, long long ldv, long long ldo, int B, int T, int Hq, int Hkv,
                    int head_dim, int causal, float scale, cudaStream_t s);
@@ -107,6 +111,20 @@ int mm_attn_bwd_tc(const void* q, const void* k, const void* v, const void* o, c
                    long long ldo, long long lddo, long long lddq, long long lddk, long long lddv, int B, int T,
                    int Hq, int Hkv, int head_dim, float scale, void* workspace, long long workspace_bytes,
                    cudaStream_t s);
+/* Packed sequences (replaces right padding, metamorph_arch.py:361-399): block-diagonal causal
+ * attention over n_seg sequences laid end to end, ONE launch for all of them. Sequence s = rows [seg_start[s],
+ * seg_start[s] + seg_len[s]) of the [total_rows, width] operands; lse is [n_seg, Hq, max_len]; work lists are int pairs
+ * (sequence, 128-row tile), heaviest first: query tiles for the forward and the dQ kernel, key tiles for dK/dV. */
+int mm_attn_fwd_tc_varlen(const void* q, const void* k, const void* v, void* o, float* lse, const int* seg_start,
+                          const int* seg_len, int n_seg, int max_len, const int* work, int n_work,
+                          long long total_rows, long long ldq, long long ldk, long long ldv, long long ldo, int Hq,
+                          int Hkv, int head_dim, float scale, cudaStream_t s);
+int mm_attn_bwd_tc_varlen(const void* q, const void* k, const void* v, const void* o, const void* dout,
+                          const float* lse, void* dq, void* dk, void* dv, const int* seg_start, const int* seg_len,
+                          int n_seg, int max_len, const int* work_q, int n_work_q, const int* work_k, int n_work_k,
+                          long long total_rows, long long ldq, long long ldk, long long ldv, long long ldo,
+                          long long lddo, long long lddq, long long lddk, long long lddv, int Hq, int Hkv,
+                          int head_dim, float scale, void* workspace, long long workspace_bytes, cudaStream_t s);
 int mm_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout, const float* lse,
                 void* dq, void* dk, void* dv, const int* seqlens, long long ldq, long long ldk, long long ldv,
                 long long ldo, long long lddo, long long lddq, long long lddk, long long lddv, int B, int T,
@@ -135,23 +153,6 @@ int mm_decode_attn(const void* qkv, long long ldqkv, void* kcache, void* vcache,
                    const float* cos_t, const float* sin_t, void* out, long long ldo, int B, int Hq, int Hkv,
                    int head_dim, int Tmax, float scale, void* workspace, long long workspace_bytes, int splits,
                    cudaStream_t s);
-/* Whole-stack decode step in one persistent kernel (csrc/decode_stack.cu): all L decoder layers of one KV-cached
- * step (HF LlamaDecoderLayer x L as driven by greedy_decode, metamorph_llama.py:526-535) with a continuous TMA
- * weight stream. plan_build fills a HOST buffer (tensor maps + norm pointers) that the caller copies to 128-byte
- * aligned device memory; the workspace must be zero-filled once before the first step. x [B, hidden] is updated in
- * place; K/V of the fed token are appended at pos[b]. Requires head_dim 128, hidden and heads*128 <= 4096, and
- * hidden / intermediate multiples of 64. */
-long long mm_decode_stack_plan_bytes(int n_layers);
-int mm_decode_stack_plan_build(void* plan_host, int n_layers, const void* const* wqkv, const void* const* wo,
-                               const void* const* wgu, const void* const* wd, const void* const* ln1,
-                               const void* const* ln2, int hidden, int n_heads, int n_kv_heads, int head_dim,
-                               int intermediate);
-long long mm_decode_stack_workspace_bytes(int B, int hidden, int n_heads, int n_kv_heads, int intermediate);
-long long mm_decode_stack_trace_offset(int B, int hidden, int n_heads, int n_kv_heads, int intermediate);
-int mm_decode_stack(const void* plan_dev, int n_layers, void* x, void* kcache, void* vcache,
-                    long long cache_layer_stride, const int* pos, const float* cos_t, const float* sin_t, int B,
-                    int hidden, int n_heads, int n_kv_heads, int intermediate, int Tmax, float scale, float eps,
-                    void* workspace, long long workspace_bytes, cudaStream_t s);
 int mm_kv_prefill(const void* qkv, long long ld, void* kcache, void* vcache, int B, int T, int Hq, int Hkv,
                   int head_dim, int Tmax, cudaStream_t s);
 int mm_decode_state_step(int* in_image_mode, int* total_image_tokens, int* total_output, int* finished, int* pos,

@@ -255,8 +255,7 @@ flash_fwd_kernel(FwdParams p) {
 // delta[b,h,t] = sum_c dO[t,h,c] * O[t,h,c]; one warp per (token,head)
 __global__ void attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout,
                                   float* __restrict__ delta, long long ldo, long long lddo, int B,
-                                  int T, int Hq, int dh, float delta_scale, const float* __restrict__ lse,
-                                  float* __restrict__ lse2, int Tp) {
+                                  int T, int Hq, int dh) {
   const int warps_per_block = blockDim.x >> 5, lane = threadIdx.x & 31;
   const long long total = (long long)B * T * Hq;
   for (long long w = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); w < total;
@@ -281,10 +280,7 @@ __global__ void attn_delta_kernel(const bf16* __restrict__ o, const bf16* __rest
     s = warp_sum(s);
     if (lane == 0) {
       const int b = (int)(tok / T), t = (int)(tok % T);
-      // outputs use the row pitch Tp (>= T; the tcgen05 backward bulk-loads 128-float rows at 16-byte alignment)
-      const long long off = ((long long)b * Hq + h) * Tp + t;
-      delta[off] = s * delta_scale;
-      if (lse2 != nullptr) lse2[off] = lse[((long long)b * Hq + h) * T + t] * kLog2e;   // exp2-domain copy
+      delta[((long long)b * Hq + h) * T + t] = s;
     }
   }
 }
@@ -561,27 +557,6 @@ int launch_fwd(const FwdParams& p, cudaStream_t stream) {
 }  // namespace
 
 // Shared by the mma.sync and tcgen05 backward paths (declared in common.cuh).
-int mm_attn_bwd_delta_launch(const void* o, const void* dout, float* delta, long long ldo, long long lddo,
-                             int B, int T, int Hq, int head_dim, float delta_scale, const float* lse,
-                             float* lse2, int Tp, cudaStream_t stream) {
-  const long long total = (long long)B * T * Hq;
-  long long blocks = ceil_div64(total, 8);
-  if (blocks > (long long)mm_num_sms() * 16) blocks = (long long)mm_num_sms() * 16;
-  attn_delta_kernel<<<(int)blocks, 256, 0, stream>>>((const bf16*)o, (const bf16*)dout, delta, ldo, lddo, B, T,
-                                                     Hq, head_dim, delta_scale, lse, lse2, Tp);
-  MM_CHECK_LAUNCH();
-  return MM_OK;
-}
-
-int mm_attn_bwd_convert_launch(const float* dq_accum, void* dq, long long R, int C, long long lddq,
-                               cudaStream_t stream) {
-  long long blocks = ceil_div64(R * (C / 8), 256);
-  if (blocks > (long long)mm_num_sms() * 16) blocks = (long long)mm_num_sms() * 16;
-  f32_to_bf16_rows_kernel<<<(int)blocks, 256, 0, stream>>>(dq_accum, (bf16*)dq, R, C, lddq);
-  MM_CHECK_LAUNCH();
-  return MM_OK;
-}
-
 MM_API int mm_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse,
                        const int* seqlens, long long ldq, long long ldk, long long ldv,
                        long long ldo, int B, int T, int Hq, int Hkv, int head_dim, int causal,
@@ -602,12 +577,10 @@ MM_API int mm_attn_fwd(const void* q, const void* k, const void* v, void* o, flo
   return MM_ERR_ARG;
 }
 
-// Workspace: delta [B*Hq*T] fp32 followed by dq_accum [B*T*Hq*128] fp32.
-// Workspace: delta [B*Hq*T] fp32, dq_accum [B*T*Hq*128] fp32, then (tcgen05 path) lse*log2e [B*Hq*T] fp32 + pad.
+// Workspace of the mma.sync backward (test-only comparison kernel): delta [B*Hq*T] fp32 + dq_accum [B*T*Hq*128] fp32.
 MM_API long long mm_attn_bwd_workspace_bytes(int B, int T, int Hq) {
-  const long long Tp = ((long long)T + 127) / 128 * 128;   // statistics rows padded to whole 128-query tiles
-  const long long delta = ((long long)B * Hq * Tp * 4 + 255) / 256 * 256;
-  return delta + (long long)B * T * Hq * 128 * 4 + delta + 1024;
+  const long long delta = ((long long)B * Hq * T * 4 + 255) / 256 * 256;
+  return delta + (long long)B * T * Hq * 128 * 4;
 }
 
 MM_API int mm_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout,
@@ -631,7 +604,7 @@ MM_API int mm_attn_bwd(const void* q, const void* k, const void* v, const void* 
     long long blocks = ceil_div64(total, 8);
     if (blocks > (long long)mm_num_sms() * 16) blocks = (long long)mm_num_sms() * 16;
     attn_delta_kernel<<<(int)blocks, 256, 0, stream>>>((const bf16*)o, (const bf16*)dout, delta, ldo,
-                                                       lddo, B, T, Hq, head_dim, 1.f, nullptr, nullptr, T);
+                                                       lddo, B, T, Hq, head_dim);
     MM_CHECK_LAUNCH();
   }
   BwdParams p;

@@ -55,11 +55,6 @@ int mm_pdl_enabled();
 // 2 = the small decode kernels too, 4 = L2 prefetch in the register-staged GEMM prologue, 8 = trigger dependents
 // after the main loop instead of at kernel entry
 int mm_pdl_mode();
-int mm_attn_bwd_delta_launch(const void* o, const void* dout, float* delta, long long ldo, long long lddo,
-                             int B, int T, int Hq, int head_dim, float delta_scale, const float* lse,
-                             float* lse2, int Tp, cudaStream_t stream);
-int mm_attn_bwd_convert_launch(const float* dq_accum, void* dq, long long R, int C, long long lddq,
-                               cudaStream_t stream);
 
 // ----------------------------------------------------------------------------------------------
 // Device helpers
@@ -205,13 +200,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug becomes a trap (launch failure) instead of a hung GPU box.
+// Bounded wait: a protocol bug becomes a trap (launch failure) instead of a hung GPU box. The bound is in TIME (about
+// two seconds of SM clock): one try_wait may itself block for a hardware-defined interval, so a spin count says little.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {
-      printf("mbar_wait timeout: block %d thread %d bar %u parity %u\n", (int)blockIdx.x,
-             (int)threadIdx.x, bar, parity);
+    if ((++spins & 0x3FFu) == 0 && clock64() - t0 > 4000000000ll) {
+      printf("mbar_wait timeout: block (%d,%d,%d) thread %d bar %u parity %u\n", (int)blockIdx.x, (int)blockIdx.y,
+             (int)blockIdx.z, (int)threadIdx.x, bar, parity);
       __trap();
     }
   }

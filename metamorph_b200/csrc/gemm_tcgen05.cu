@@ -70,6 +70,28 @@ __device__ __forceinline__ uint64_t make_desc_base(bool mn_major) {
   return (lbo << 16) | (sbo << 32) | (1ull << 46) | (2ull << 61);
 }
 
+// L2 eviction-priority hints for the operand streams (TMA .L2::cache_hint). Within one rasterisation group the A panel
+// (group_m row-blocks x K) is re-read by every column-block of the sweep -> keep it (evict_last); a B column-block is
+// consumed by the concurrently running tiles of one wave and not touched again before the next group -> evict_first.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t smem_dst, const void* tmap, uint32_t bar, int32_t c_inner,
+                                                 int32_t c_outer, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c_inner), "r"(c_outer), "l"(policy)
+      : "memory");
+}
+
 // Fused epilogue for one 32-column accumulator chunk held by one thread (one output row).
 __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, float (&v)[32], int row, bool row_ok,
                                                int col0, int N) {
@@ -426,6 +448,14 @@ __device__ __forceinline__ void tma_load_2d_2sm(uint32_t smem_dst, const void* t
       "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar & 0xFEFFFFFFu), "r"(c_inner), "r"(c_outer)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_2sm_hint(uint32_t smem_dst, const void* tmap, uint32_t bar,
+                                                     int32_t c_inner, int32_t c_outer, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar & 0xFEFFFFFFu), "r"(c_inner), "r"(c_outer), "l"(policy)
+      : "memory");
+}
 __device__ __forceinline__ void umma_bf16_ss_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
                                                  uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -445,17 +475,50 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
       : "memory");
 }
 
+// ---- cluster launch control (Blackwell work stealing): a running cluster atomically cancels a cluster of the SAME grid
+// that has not been launched yet and computes its tile. The 16-byte response lands (multicast) at the same shared-memory
+// offset of every CTA of the cluster and completes 16 tx-bytes on each CTA's mbarrier at the same offset.
+__device__ __forceinline__ void clc_try_cancel_multicast(uint32_t resp, uint32_t bar) {
+  asm volatile(
+      "clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.multicast::cluster::all.b128 "
+      "[%0], [%1];" ::"r"(resp), "r"(bar)
+      : "memory");
+}
+// -> first CTA index (x) of the cancelled cluster, or -1 when nothing was left to cancel
+__device__ __forceinline__ int clc_response_ctaid_x(uint32_t resp) {
+  uint32_t x, ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b128 r;\n"
+      "ld.shared.b128 r, [%2];\n"
+      "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p, r;\n"
+      "selp.u32 %1, 1, 0, p;\n"
+      "mov.u32 %0, 0;\n"
+      "@p clusterlaunchcontrol.query_cancel.get_first_ctaid.v4.b32.b128 {%0, _, _, _}, r;\n"
+      "}\n"
+      : "=r"(x), "=r"(ok)
+      : "r"(resp)
+      : "memory");
+  return ok ? (int)x : -1;
+}
+
 constexpr int BN2 = 256;             // cluster tile N
+constexpr int kClcStages = 3;        // tile-id responses in flight / not yet read by the slowest role
 constexpr int kStages2 = 6;
 constexpr int kA2Bytes = BM * BK * 2;          // this CTA's 128 rows of A
 constexpr int kB2Bytes = (BN2 / 2) * BK * 2;   // this CTA's 128 columns of B
 constexpr int kStage2Bytes = kA2Bytes + kB2Bytes;
-constexpr int kSmem2Bytes = kStages2 * kStage2Bytes + 1024 + 256;
+constexpr int kSmem2Bytes = kStages2 * kStage2Bytes + 1024 + 384;   // + alignment slack + barriers / CLC responses
 
-template <bool A_MN, bool B_MN>
+// Tile schedule. DYN = false: static persistent (cluster c computes tiles c, c + #clusters, ...). DYN = true (default):
+// the grid holds ONE cluster per tile and every resident cluster keeps stealing not-yet-launched clusters through
+// cluster launch control, so an SM pair that starts late or runs slow — it shares its SMs / HBM with the NCCL channels
+// and the AdamW of the previous layer's gradient bucket — simply computes fewer tiles instead of holding up its wave.
+template <bool A_MN, bool B_MN, bool DYN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                         const __grid_constant__ CUtensorMap tmap_b, int M, int N, int K, int group_m,
+                         const __grid_constant__ CUtensorMap tmap_b, int M, int N, int K, int group_m, int l2_hint,
                          EpiParams ep) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -467,6 +530,9 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const uint32_t tmem_slot = bar_base + 8u * (2 * kStages2 + 4);
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  auto clc_full = [&](int c) { return bar_base + 8u * (2 * kStages2 + 5 + c); };
+  auto clc_empty = [&](int c) { return bar_base + 8u * (2 * kStages2 + 5 + kClcStages + c); };
+  auto clc_resp = [&](int c) { return bar_base + 8u * (2 * kStages2 + 6 + 2 * kClcStages) + 16u * c; };   // 16-byte aligned
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -489,6 +555,10 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), 8);
     }
+    for (int c = 0; c < kClcStages; ++c) {
+      mbar_init(clc_full(c), 1);     // this CTA's producer arms it (arrive.expect_tx 16), the response completes it
+      mbar_init(clc_empty(c), 11);   // (leader's only) producer + MMA + 4 epilogue warps here, producer + 4 warps in the peer
+    }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -510,12 +580,41 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
     m_blk = first_m + (r % gsz);
     n_blk = r / gsz;
   };
+  // Every role walks the same tile sequence. Static: t += #clusters. Dynamic: the producer thread of each CTA arms
+  // clc_full[c] before it starts a tile and the leader's producer issues the steal; every role then reads the response
+  // when it is done with its part of the current tile and releases the slot on the LEADER's clc_empty[c].
+  auto next_tile = [&](int t, int& c, uint32_t& cph, bool one_thread) -> int {
+    if constexpr (!DYN) {
+      t += num_clusters;
+      return t < num_tiles ? t : -1;
+    } else {
+      mbar_wait(clc_full(c), cph);
+      const int x = clc_response_ctaid_x(clc_resp(c));
+      fence_proxy_async_smem();                  // the slot is rewritten by the async proxy
+      if (!one_thread) __syncwarp();
+      if (one_thread || lane == 0) {
+        if (leader) mbar_arrive(clc_empty(c));
+        else mbar_arrive_remote(clc_empty(c), 0);
+      }
+      if (++c == kClcStages) { c = 0; cph ^= 1; }
+      return x < 0 ? -1 : (x >> 1);
+    }
+  };
 
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
     int s = 0;
     uint32_t phase = 0;
-    for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+    const uint64_t pol_a = l2_policy_evict_last(), pol_b = l2_policy_evict_first();
+    int cq = 0, cc = 0;                 // response slot being requested / consumed
+    uint32_t cqph = 0, ccph = 0;
+    for (int t = cluster_id; t >= 0 && t < num_tiles;) {
+      if constexpr (DYN) {              // ask for the NEXT tile before streaming this one
+        if (leader) mbar_wait(clc_empty(cq), cqph ^ 1);     // every role of both CTAs has read the slot's previous use
+        mbar_arrive_expect_tx(clc_full(cq), 16);
+        if (leader) clc_try_cancel_multicast(clc_resp(cq), clc_full(cq));
+        if (++cq == kClcStages) { cq = 0; cqph ^= 1; }
+      }
       int m_blk, n_blk;
       tile_coords(t, m_blk, n_blk);
       const int m0 = m_blk * 2 * BM + (int)rank * BM;
@@ -527,22 +626,40 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
         if (leader) mbar_arrive_expect_tx(full_bar(s), 2 * kStage2Bytes);
         else mbar_arrive_remote(full_bar(s), 0);
         const int k0 = kb * BK;
-        if constexpr (!A_MN) {
-          tma_load_2d_2sm(sa, &tmap_a, full_bar(s), k0, m0);
-        } else {
+        if (l2_hint) {
+          if constexpr (!A_MN) {
+            tma_load_2d_2sm_hint(sa, &tmap_a, full_bar(s), k0, m0, pol_a);
+          } else {
 #pragma unroll
-          for (int j = 0; j < BM / 64; ++j)
-            tma_load_2d_2sm(sa + j * (BK * 128), &tmap_a, full_bar(s), m0 + 64 * j, k0);
-        }
-        if constexpr (!B_MN) {
-          tma_load_2d_2sm(sb, &tmap_b, full_bar(s), k0, n0);
-        } else {
+            for (int j = 0; j < BM / 64; ++j)
+              tma_load_2d_2sm_hint(sa + j * (BK * 128), &tmap_a, full_bar(s), m0 + 64 * j, k0, pol_a);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d_2sm_hint(sb, &tmap_b, full_bar(s), k0, n0, pol_b);
+          } else {
 #pragma unroll
-          for (int j = 0; j < BN2 / 2 / 64; ++j)
-            tma_load_2d_2sm(sb + j * (BK * 128), &tmap_b, full_bar(s), n0 + 64 * j, k0);
+            for (int j = 0; j < BN2 / 2 / 64; ++j)
+              tma_load_2d_2sm_hint(sb + j * (BK * 128), &tmap_b, full_bar(s), n0 + 64 * j, k0, pol_b);
+          }
+        } else {
+          if constexpr (!A_MN) {
+            tma_load_2d_2sm(sa, &tmap_a, full_bar(s), k0, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)
+              tma_load_2d_2sm(sa + j * (BK * 128), &tmap_a, full_bar(s), m0 + 64 * j, k0);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d_2sm(sb, &tmap_b, full_bar(s), k0, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN2 / 2 / 64; ++j)
+              tma_load_2d_2sm(sb + j * (BK * 128), &tmap_b, full_bar(s), n0 + 64 * j, k0);
+          }
         }
         if (++s == kStages2) { s = 0; phase ^= 1; }
       }
+      t = next_tile(t, cc, ccph, true);
     }
   } else if (warp == 1 && lane == 0 && leader) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
@@ -557,7 +674,9 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+    int cc = 0;
+    uint32_t ccph = 0;
+    for (int t = cluster_id; t >= 0 && t < num_tiles; t = next_tile(t, cc, ccph, true)) {
       mbar_wait(tempty_bar(acc), acc_phase ^ 1);
       tcgen05_fence_after();
       const uint32_t tmem_d = tmem_base + acc * BN2;
@@ -583,7 +702,9 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const int q = warp & 3;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+    int cc = 0;
+    uint32_t ccph = 0;
+    for (int t = cluster_id; t >= 0 && t < num_tiles; t = next_tile(t, cc, ccph, false)) {
       int m_blk, n_blk;
       tile_coords(t, m_blk, n_blk);
       const int row = m_blk * 2 * BM + (int)rank * BM + q * 32 + lane;
@@ -668,6 +789,20 @@ int make_tmap(CUtensorMap* tm, const void* base, long long inner, long long oute
   return MM_OK;
 }
 
+// experiment switches, read ONCE per process (never on the launch path)
+int env_group_m() {
+  static const int v = [] { const char* e = getenv("MM_GEMM_GM"); return e ? atoi(e) : 0; }();
+  return v;
+}
+int env_dynamic_tiles() {   // MM_GEMM_DYNAMIC=0 selects the static persistent schedule of the 2-CTA kernel (A/B measurements)
+  static const int v = [] { const char* e = getenv("MM_GEMM_DYNAMIC"); return e ? atoi(e) : 1; }();
+  return v;
+}
+int env_l2_hint() {   // MM_GEMM_L2HINT=0 disables the TMA L2 eviction hints of the 2-CTA kernel
+  static const int v = [] { const char* e = getenv("MM_GEMM_L2HINT"); return e ? atoi(e) : 1; }();
+  return v;
+}
+
 template <int BN, bool A_MN, bool B_MN>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EpiParams& ep,
            cudaStream_t stream) {
@@ -689,16 +824,16 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, co
   long long gm = (32ll << 20) / ((long long)BM * K * 2);
   if (gm < 17) gm = 17;
   if (gm > 64) gm = 64;
-  if (const char* e = getenv("MM_GEMM_GM")) gm = atoi(e) > 0 ? atoi(e) : gm;   // rasterisation experiments
+  if (env_group_m() > 0) gm = env_group_m();   // rasterisation experiments (MM_GEMM_GM, read once)
   kern<<<grid, kThreads, Cfg<BN>::kSmemBytes, stream>>>(ta, tb, M, N, K, (int)gm, ep);
   MM_CHECK_LAUNCH();
   return MM_OK;
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, bool DYN>
 int launch2(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EpiParams& ep,
             cudaStream_t stream) {
-  auto kern = gemm_tcgen05_2cta_kernel<A_MN, B_MN>;
+  auto kern = gemm_tcgen05_2cta_kernel<A_MN, B_MN, DYN>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
@@ -707,13 +842,13 @@ int launch2(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, c
   MM_CHECK_CUDA(attr_err);
   const int num_tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN2 - 1) / BN2);
   int clusters = mm_num_sms() / 2;
-  if (clusters > num_tiles) clusters = num_tiles;
+  if (clusters > num_tiles || DYN) clusters = num_tiles;     // dynamic: one cluster per tile, the resident ones steal the rest
   // same rule as the 1-CTA launcher with 256-row blocks and 74 concurrent cluster tiles (square wave: 8 x 9)
   long long gm = (32ll << 20) / ((long long)2 * BM * K * 2);
   if (gm < 8) gm = 8;
   if (gm > 32) gm = 32;
-  if (const char* e = getenv("MM_GEMM_GM")) gm = atoi(e) > 0 ? atoi(e) : gm;   // rasterisation experiments
-  kern<<<2 * clusters, kThreads, kSmem2Bytes, stream>>>(ta, tb, M, N, K, (int)gm, ep);
+  if (env_group_m() > 0) gm = env_group_m();   // rasterisation experiments (MM_GEMM_GM, read once)
+  kern<<<2 * clusters, kThreads, kSmem2Bytes, stream>>>(ta, tb, M, N, K, (int)gm, env_l2_hint(), ep);
   MM_CHECK_LAUNCH();
   return MM_OK;
 }
@@ -775,9 +910,14 @@ MM_API int mm_gemm_bf16(const void* A, const void* B, void* C, const void* bias,
     ep2.resid = reinterpret_cast<const bf16*>(resid); ep2.ldr = ldr;
     ep2.aux = reinterpret_cast<bf16*>(aux); ep2.ld_aux = ld_aux;
     ep2.epi = epilogue; ep2.out_f32 = out_f32; ep2.accumulate = accumulate; ep2.alpha = alpha;
-    if (!a_mn_major && !b_mn_major) return launch2<false, false>(ta2, tb2, (int)M, (int)N, (int)K, ep2, stream);
-    if (!a_mn_major && b_mn_major) return launch2<false, true>(ta2, tb2, (int)M, (int)N, (int)K, ep2, stream);
-    return launch2<true, true>(ta2, tb2, (int)M, (int)N, (int)K, ep2, stream);
+    if (env_dynamic_tiles()) {
+      if (!a_mn_major && !b_mn_major) return launch2<false, false, true>(ta2, tb2, (int)M, (int)N, (int)K, ep2, stream);
+      if (!a_mn_major && b_mn_major) return launch2<false, true, true>(ta2, tb2, (int)M, (int)N, (int)K, ep2, stream);
+      return launch2<true, true, true>(ta2, tb2, (int)M, (int)N, (int)K, ep2, stream);
+    }
+    if (!a_mn_major && !b_mn_major) return launch2<false, false, false>(ta2, tb2, (int)M, (int)N, (int)K, ep2, stream);
+    if (!a_mn_major && b_mn_major) return launch2<false, true, false>(ta2, tb2, (int)M, (int)N, (int)K, ep2, stream);
+    return launch2<true, true, false>(ta2, tb2, (int)M, (int)N, (int)K, ep2, stream);
   }
   int bn = 256;
   if (force_bn == 128 || force_bn == 256) {

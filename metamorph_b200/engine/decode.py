@@ -8,7 +8,6 @@ only reset by <image_end>), but (a) with a KV cache instead of re-running the gr
 """
 from __future__ import annotations
 
-import os
 from typing import Optional
 
 import torch
@@ -23,10 +22,6 @@ class DecodeEngine:
     def __init__(self, model):
         self.m = model
         self.use_cuda_graph = True
-        # Opt-in (MM_DECODE_STACK=1 / use_stack_kernel=True): one persistent kernel for all decoder layers of a step
-        # (csrc/decode_stack.cu). Parity-tested, but on B200 it does not beat the per-op kernels yet (4.44 vs 4.27
-        # ms/step on the 512-position batch-8 decode, profiles/r01_decode_stack_kernel.txt), so they stay the default.
-        self.use_stack_kernel = os.environ.get("MM_DECODE_STACK", "0") == "1"
 
     @torch.no_grad()
     def generate(self, inputs_embeds: torch.Tensor, prompt_lens: Optional[torch.Tensor] = None,
@@ -100,18 +95,9 @@ class DecodeEngine:
         ev[0].record()                                   # prefill done (enqueued) -> decode steps start
         heads_and_state(h_last, 0)
 
-        stack_plan = None
-        if self.use_stack_kernel and ops.decode_stack_supported(H, Hq, Hkv, dh, d.intermediate, B, Tmax):
-            stack_plan = ops.DecodeStackPlan(layers, H, Hq, Hkv, dh, d.intermediate, B, dev)
-        self.last_used_stack_kernel = stack_plan is not None
-        self.last_stack_plan = stack_plan
-
         def one_step_body():
             # position of the token being fed = pos - 1 (the state step already advanced pos)
-            cur_pos = st["pos"] - 1
-            if stack_plan is not None:
-                return ops.decode_stack(stack_plan, xin, kc, vc, cur_pos, stack.cos, stack.sin, stack.scale, d.rms_eps)
-            return decoder_stack_step(layers, xin, kc, vc, cur_pos, stack)
+            return decoder_stack_step(layers, xin, kc, vc, st["pos"] - 1, stack)
 
         # One captured CUDA graph is replayed for every step (launch-bound inner loop): all per-step state,
         # including the index into the forced-token schedule, lives in device memory.

@@ -248,11 +248,17 @@ class HotPath:
         x = ops.interleave_gather(model.embed_tokens.weight.data, ar_feats, row_map)
         pos = plan.position_ids.reshape(-1).to(torch.int32).to(dev, non_blocking=True)
         seqlens = plan.seqlens.to(dev, non_blocking=True)
-        if plan.padding_side != "right" and bool((plan.seqlens != T).any()):
-            raise NotImplementedError("left padding with ragged lengths is not supported by the fused attention")
         flat_segments = None
         if plan.segments is not None:
             flat_segments = [(r * T + off, n) for r, segs in enumerate(plan.segments) for off, n in segs]
+        elif plan.padding_side != "right" and bool((plan.seqlens != T).any()):
+            # left padding (tokenizer_padding_side == "left", metamorph_arch.py:373-386): sample b occupies the LAST
+            # seqlens[b] rows of its batch row -> one segment per sample for the segment-aware attention kernels
+            flat_segments = [(b * T + T - int(n), int(n)) for b, n in enumerate(plan.seqlens.tolist()) if int(n) > 0]
+            # the reference forwards position_ids=None (metamorph_arch.py:405-406), so HF LlamaModel numbers the rows of
+            # the padded batch 0..T-1 (cache_position), pads included; RoPE only sees differences, but the bf16-rounded
+            # cos/sin entries are those of the absolute row index
+            pos = torch.arange(T, dtype=torch.int32).repeat(B).to(dev, non_blocking=True)
         ctx = StackContext(B=B, T=T, pos=pos, seqlens=seqlens, segments=flat_segments)
         stack = m.stack
         layers = [l.weights() for l in model.layers]

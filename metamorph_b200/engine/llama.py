@@ -102,9 +102,11 @@ class StackContext:
     pos: torch.Tensor            # int32 [B*T]
     seqlens: Optional[torch.Tensor]
     saved: List[LayerSaved] = field(default_factory=list)
-    # sequence packing: flat (first row, length) of every sample in the [B*T] token dimension; attention runs per
-    # segment (block-diagonal causal), every other kernel is per token and does not care
+    # sequence packing: flat (first row, length) of every sample in the [B*T] token dimension; attention is
+    # block-diagonal causal over these segments (ONE launch per layer through the segment tables), every other kernel is
+    # per token and does not care
     segments: Optional[List[tuple]] = None
+    seg_tables: Optional["ops.SegmentTables"] = None
     x_final_in: Optional[torch.Tensor] = None  # input of the final norm
 
 
@@ -137,12 +139,10 @@ class LlamaStack:
             attn, lse = ops.attn_fwd(q, k, v, B, T, Hq, Hkv, dh, True, self.scale, seqlens=ctx.seqlens,
                                      need_lse=save)
         else:
+            if ctx.seg_tables is None:
+                ctx.seg_tables = ops.SegmentTables(ctx.segments, x.device)
             attn = torch.zeros((x.shape[0], Hq * dh), dtype=torch.bfloat16, device=x.device)   # pad rows stay finite
-            lse = []
-            for r0, n in ctx.segments:
-                _, l = ops.attn_fwd(q[r0:r0 + n], k[r0:r0 + n], v[r0:r0 + n], 1, n, Hq, Hkv, dh, True, self.scale,
-                                    out=attn[r0:r0 + n], need_lse=save)
-                lse.append(l)
+            _, lse = ops.attn_fwd_varlen(q, k, v, ctx.seg_tables, Hq, Hkv, dh, self.scale, out=attn, need_lse=save)
         h_mid = ops.gemm(attn, w.wo, resid=x, epilogue=ops.EPI_RESID)
         n2 = ops.rmsnorm(h_mid, w.ln2, d.rms_eps)
         gu = torch.empty((x.shape[0], 2 * d.intermediate), dtype=torch.bfloat16, device=x.device) \
@@ -210,12 +210,10 @@ class LlamaStack:
                                          B, T, Hq, Hkv, dh, self.scale, seqlens=ctx.seqlens,
                                          workspace=self._attn_ws)
         else:
-            dqkv = torch.zeros_like(s.qkv)
-            dq, dk, dv = dqkv[:, :Hq * dh], dqkv[:, Hq * dh:(Hq + Hkv) * dh], dqkv[:, (Hq + Hkv) * dh:]
-            for (r0, n), lse in zip(ctx.segments, s.lse):
-                self._attn_ws = ops.attn_bwd(q[r0:r0 + n], k[r0:r0 + n], v[r0:r0 + n], s.attn[r0:r0 + n],
-                                             dattn[r0:r0 + n], lse, dq[r0:r0 + n], dk[r0:r0 + n], dv[r0:r0 + n],
-                                             1, n, Hq, Hkv, dh, self.scale, workspace=self._attn_ws)
+            dqkv = torch.zeros_like(s.qkv)                    # rows between / after the segments get no gradient
+            self._attn_ws = ops.attn_bwd_varlen(q, k, v, s.attn, dattn, s.lse, dqkv[:, :Hq * dh],
+                                                dqkv[:, Hq * dh:(Hq + Hkv) * dh], dqkv[:, (Hq + Hkv) * dh:],
+                                                ctx.seg_tables, Hq, Hkv, dh, self.scale, workspace=self._attn_ws)
         del dattn
         ops.rope_(dqkv, ctx.pos, self.cos, self.sin, Hq + Hkv, dh, backward=True)
         if need_wgrad:

@@ -142,13 +142,25 @@ class SiglipVisionTransformerParams(nn.Module):
         kpad = 640
         wpe = torch.zeros(c.hidden_size, kpad, dtype=pe.weight.dtype, device=pe.weight.device)
         wpe[:, :3 * c.patch_size * c.patch_size] = pe.weight.data.reshape(c.hidden_size, -1)
+        # Attention runs on the tcgen05 flash kernel (head_dim 128, csrc/attention_tc.cu): every head of width dh (72 for
+        # SO400M) is laid out in a 128-wide slot whose tail is exactly zero — zero rows in the fused QKV weight/bias, zero
+        # columns in out_proj — so QK^T, softmax and the visible part of PV are those of the dh-wide heads
+        # (HF modeling_siglip.py:229-249), with no pad/unpad pass over the activations.
+        heads, W = c.num_attention_heads, c.hidden_size
+        dh, dp = W // heads, 128
+        assert dh <= dp, "SigLIP head_dim above 128 is not supported by the attention kernel"
         layers = []
         for l in self.encoder.layers:
             a = l.self_attn
-            layers.append(dict(
-                wqkv=torch.cat([a.q_proj.weight.data, a.k_proj.weight.data, a.v_proj.weight.data], 0).contiguous(),
-                bqkv=torch.cat([a.q_proj.bias.data, a.k_proj.bias.data, a.v_proj.bias.data], 0).contiguous()))
-        self._packed = dict(wpe=wpe, kpad=kpad, layers=layers)
+            wqkv = torch.zeros(3 * heads * dp, W, dtype=wpe.dtype, device=wpe.device)
+            bqkv = torch.zeros(3 * heads * dp, dtype=wpe.dtype, device=wpe.device)
+            for j, proj in enumerate((a.q_proj, a.k_proj, a.v_proj)):
+                wqkv.view(3, heads, dp, W)[j, :, :dh] = proj.weight.data.view(heads, dh, W)
+                bqkv.view(3, heads, dp)[j, :, :dh] = proj.bias.data.view(heads, dh)
+            wo = torch.zeros(W, heads * dp, dtype=wpe.dtype, device=wpe.device)
+            wo.view(W, heads, dp)[:, :, :dh] = a.out_proj.weight.data.view(W, heads, dh)
+            layers.append(dict(wqkv=wqkv, bqkv=bqkv, wo=wo))
+        self._packed = dict(wpe=wpe, kpad=kpad, layers=layers, head_slot=dp)
 
     def forward_features(self, images: torch.Tensor, n_layers_to_run: int) -> torch.Tensor:
         """images [N,3,S,S] -> hidden state after `n_layers_to_run` encoder layers, [N*P, width]."""
@@ -163,16 +175,15 @@ class SiglipVisionTransformerParams(nn.Module):
         x = ops.gemm(ops.im2col_patch14(images.contiguous(), pk["kpad"]), pk["wpe"],
                      bias=self.embeddings.patch_embedding.bias.data, epilogue=ops.EPI_BIAS)
         ops.add_pos_emb_(x, self.embeddings.position_embedding.weight.data)
-        W = c.hidden_size
         scale = dh ** -0.5
+        Wp = heads * pk["head_slot"]                         # width of the padded q / k / v blocks
         for li in range(n_layers_to_run):
             l, pl = self.encoder.layers[li], pk["layers"][li]
             h = ops.layernorm(x, l.layer_norm1.weight.data, l.layer_norm1.bias.data, c.layer_norm_eps)
             qkv = ops.gemm(h, pl["wqkv"], bias=pl["bqkv"], epilogue=ops.EPI_BIAS)
-            attn, _ = ops.attn_fwd(qkv[:, :W], qkv[:, W:2 * W], qkv[:, 2 * W:], n, P, heads, heads, dh,
-                                   False, scale, need_lse=False)
-            x = ops.gemm(attn, l.self_attn.out_proj.weight.data, bias=l.self_attn.out_proj.bias.data,
-                         resid=x, epilogue=ops.EPI_BIAS_RESID)
+            attn, _ = ops.attn_fwd(qkv[:, :Wp], qkv[:, Wp:2 * Wp], qkv[:, 2 * Wp:], n, P, heads, heads, pk["head_slot"],
+                                   False, scale, need_lse=False, tc=True)
+            x = ops.gemm(attn, pl["wo"], bias=l.self_attn.out_proj.bias.data, resid=x, epilogue=ops.EPI_BIAS_RESID)
             h = ops.layernorm(x, l.layer_norm2.weight.data, l.layer_norm2.bias.data, c.layer_norm_eps)
             h = ops.gemm(h, l.mlp.fc1.weight.data, bias=l.mlp.fc1.bias.data, epilogue=ops.EPI_BIAS_GELU_TANH)
             x = ops.gemm(h, l.mlp.fc2.weight.data, bias=l.mlp.fc2.bias.data, resid=x, epilogue=ops.EPI_BIAS_RESID)

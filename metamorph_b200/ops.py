@@ -312,17 +312,75 @@ def attn_bwd(q, k, v, o, dout, lse, dq, dk, dv, B, T, Hq, Hkv, head_dim, scale, 
              workspace=None, tc=None):
     require_cuda(q, k, v, o, dout, lse, dq, dk, dv)
     from ._lib import lib
-    fn = lib().mm_attn_bwd_workspace_bytes
+    use_tc = ATTN_BWD_TC if tc is None else tc   # tc=False: the mma.sync kernel, kept as a test-only comparison
+    fn = lib().mm_attn_bwd_tc_workspace_bytes if use_tc else lib().mm_attn_bwd_workspace_bytes
     fn.restype = ctypes_ll
     need = fn(c_int(B), c_int(T), c_int(Hq))
     if workspace is None or workspace.numel() < need:
         workspace = torch.empty(need, dtype=torch.uint8, device=q.device)
-    use_tc = ATTN_BWD_TC if tc is None else tc   # tc=False: the mma.sync kernel, kept as a test-only comparison
     call("mm_attn_bwd_tc" if use_tc else "mm_attn_bwd", ptr(q), ptr(k), ptr(v), ptr(o), ptr(dout), ptr(lse), ptr(dq), ptr(dk), ptr(dv),
          ptr(seqlens), ll(q.stride(0)), ll(k.stride(0)), ll(v.stride(0)), ll(o.stride(0)),
          ll(dout.stride(0)), ll(dq.stride(0)), ll(dk.stride(0)), ll(dv.stride(0)), c_int(B), c_int(T),
          c_int(Hq), c_int(Hkv), c_int(head_dim), c_float(scale), ptr(workspace), ll(workspace.numel()),
          stream_ptr())
+    return workspace
+
+
+class SegmentTables:
+    """Device tables of a packed batch for the one-launch block-diagonal attention kernels:
+    sequence s occupies rows [start[s], start[s] + length[s]) of the token dimension. The work lists name every
+    128-row tile that exists — (sequence, query tile) for the forward / dQ kernels, (sequence, key tile) for the dK/dV
+    kernel — heaviest first (a query tile attends to tile+1 key tiles, a key tile is visited by n_tiles-tile query tiles)."""
+
+    def __init__(self, segments, device):
+        self.segments = [(int(a), int(n)) for a, n in segments]
+        self.n_seg = len(self.segments)
+        self.max_len = max(n for _, n in self.segments)
+        self.total = sum(n for _, n in self.segments)
+        wq, wk = [], []
+        for s, (_, n) in enumerate(self.segments):
+            nt = (n + 127) // 128
+            wq += [(t + 1, s, t) for t in range(nt)]
+            wk += [(nt - t, s, t) for t in range(nt)]
+        wq.sort(key=lambda x: -x[0])
+        wk.sort(key=lambda x: -x[0])
+        host = torch.tensor([a for a, _ in self.segments] + [n for _, n in self.segments] +
+                            [v for _, s_, t in wq for v in (s_, t)] + [v for _, s_, t in wk for v in (s_, t)],
+                            dtype=torch.int32)
+        dev = host.to(device, non_blocking=True)
+        S = self.n_seg
+        self.start, self.length = dev[:S], dev[S:2 * S]
+        self.n_work_q, self.n_work_k = len(wq), len(wk)
+        self.work_q = dev[2 * S:2 * S + 2 * len(wq)]
+        self.work_k = dev[2 * S + 2 * len(wq):]
+
+
+def attn_fwd_varlen(q, k, v, seg: SegmentTables, Hq, Hkv, head_dim, scale, out, need_lse=True):
+    """Block-diagonal causal attention over the packed sequences of `seg` in ONE launch (tcgen05 kernel).
+    Rows outside every sequence are not written. Returns (out, lse [n_seg, Hq, max_len])."""
+    require_cuda(q, k, v, out)
+    assert q.stride(1) == 1 and k.stride(1) == 1 and v.stride(1) == 1 and head_dim == 128
+    lse = torch.empty((seg.n_seg, Hq, seg.max_len), dtype=torch.float32, device=q.device) if need_lse else None
+    call("mm_attn_fwd_tc_varlen", ptr(q), ptr(k), ptr(v), ptr(out), ptr(lse), ptr(seg.start), ptr(seg.length),
+         c_int(seg.n_seg), c_int(seg.max_len), ptr(seg.work_q), c_int(seg.n_work_q), ll(q.shape[0]), ll(q.stride(0)),
+         ll(k.stride(0)), ll(v.stride(0)), ll(out.stride(0)), c_int(Hq), c_int(Hkv), c_int(head_dim), c_float(scale),
+         stream_ptr())
+    return out, lse
+
+
+def attn_bwd_varlen(q, k, v, o, dout, lse, dq, dk, dv, seg: SegmentTables, Hq, Hkv, head_dim, scale, workspace=None):
+    require_cuda(q, k, v, o, dout, lse, dq, dk, dv)
+    from ._lib import lib
+    fn = lib().mm_attn_bwd_tc_workspace_bytes
+    fn.restype = ctypes_ll
+    need = fn(c_int(seg.n_seg), c_int(seg.max_len), c_int(Hq))
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=q.device)
+    call("mm_attn_bwd_tc_varlen", ptr(q), ptr(k), ptr(v), ptr(o), ptr(dout), ptr(lse), ptr(dq), ptr(dk), ptr(dv),
+         ptr(seg.start), ptr(seg.length), c_int(seg.n_seg), c_int(seg.max_len), ptr(seg.work_q), c_int(seg.n_work_q),
+         ptr(seg.work_k), c_int(seg.n_work_k), ll(q.shape[0]), ll(q.stride(0)), ll(k.stride(0)), ll(v.stride(0)),
+         ll(o.stride(0)), ll(dout.stride(0)), ll(dq.stride(0)), ll(dk.stride(0)), ll(dv.stride(0)), c_int(Hq),
+         c_int(Hkv), c_int(head_dim), c_float(scale), ptr(workspace), ll(workspace.numel()), stream_ptr())
     return workspace
 
 
@@ -364,69 +422,6 @@ def decode_attn(qkv, kcache, vcache, pos, cos, sin, Hq, Hkv, head_dim, scale, ou
          ptr(sin), ptr(out), ll(out.stride(0)), c_int(B), c_int(Hq), c_int(Hkv), c_int(head_dim),
          c_int(Tmax), c_float(scale), ptr(ws), ll(ws.numel()), c_int(splits), stream_ptr())
     return out
-
-
-class DecodeStackPlan:
-    """Device-resident launch plan of the one-kernel decode step (csrc/decode_stack.cu): TMA tensor maps of every
-    layer's four weight matrices + norm-weight pointers, and the zero-initialised activation / barrier workspace."""
-
-    def __init__(self, layers, hidden, n_heads, n_kv_heads, head_dim, intermediate, batch, device):
-        from ._lib import lib
-        L = len(layers)
-        fnb = lib().mm_decode_stack_plan_bytes
-        fnb.restype = ctypes_ll
-        nbytes = int(fnb(c_int(L)))
-        host = (_ctypes.c_uint8 * (nbytes + 128))()
-        base = _ctypes.addressof(host)
-        aligned = (base + 127) & ~127
-        arr_t = _ctypes.c_void_p * L
-
-        def arr(ts):
-            require_cuda(*ts)
-            for t in ts:
-                assert t.is_contiguous() and t.dtype == torch.bfloat16
-            return arr_t(*[t.data_ptr() for t in ts])
-
-        call("mm_decode_stack_plan_build", c_void_p(aligned), c_int(L), arr([w.wqkv for w in layers]),
-             arr([w.wo for w in layers]), arr([w.wgu for w in layers]), arr([w.wd for w in layers]),
-             arr([w.ln1 for w in layers]), arr([w.ln2 for w in layers]), c_int(hidden), c_int(n_heads),
-             c_int(n_kv_heads), c_int(head_dim), c_int(intermediate))
-        blob = torch.frombuffer(host, dtype=torch.uint8, count=nbytes, offset=aligned - base).clone()
-        self.plan = blob.to(device)
-        self._keep = layers                     # the plan holds raw pointers into these tensors
-        fnw = lib().mm_decode_stack_workspace_bytes
-        fnw.restype = ctypes_ll
-        wbytes = int(fnw(c_int(batch), c_int(hidden), c_int(n_heads), c_int(n_kv_heads), c_int(intermediate)))
-        self.workspace = torch.zeros(wbytes, dtype=torch.uint8, device=device)
-        self.dims = (L, hidden, n_heads, n_kv_heads, intermediate, batch)
-
-
-def decode_stack(plan: DecodeStackPlan, x, kcache, vcache, pos, cos, sin, scale, eps):
-    """One KV-cached decode step through all layers in one persistent kernel; x [B, H] is updated in place.
-    kcache / vcache: [L, B, Hkv, Tmax, 128]."""
-    require_cuda(x, kcache, vcache, pos, cos, sin)
-    L, H, Hq, Hkv, inter, batch = plan.dims
-    assert x.shape[0] == batch and x.is_contiguous() and kcache.is_contiguous() and vcache.is_contiguous()
-    call("mm_decode_stack", ptr(plan.plan), c_int(L), ptr(x), ptr(kcache), ptr(vcache), ll(kcache.stride(0)),
-         ptr(pos), ptr(cos), ptr(sin), c_int(batch), c_int(H), c_int(Hq), c_int(Hkv), c_int(inter),
-         c_int(kcache.shape[3]), c_float(scale), c_float(eps), ptr(plan.workspace), ll(plan.workspace.numel()),
-         stream_ptr())
-    return x
-
-
-def decode_stack_supported(hidden, n_heads, n_kv_heads, head_dim, intermediate, batch, t_max) -> bool:
-    """Shape envelope of the one-kernel step; outside it the engine uses the per-op CUDA kernels."""
-    if head_dim != 128 or hidden % 64 or intermediate % 64:
-        return False
-    if hidden > 4096 or n_heads * head_dim > 4096 or n_heads % n_kv_heads or batch > 8:
-        return False
-    g = n_heads // n_kv_heads
-    if g not in (1, 2, 4, 8):
-        return False
-    sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
-    splits = max(1, min(16, sms // (batch * n_kv_heads)))
-    cpad = ((t_max + splits - 1) // splits + 4) & ~3
-    return (g * 128 + 256 + 8 * g * 128 + 16 + g * cpad) * 4 <= 8 * (4096 * 2 + 64)
 
 
 def kv_prefill(qkv, kcache, vcache, B, T, Hq, Hkv, head_dim):

@@ -173,6 +173,34 @@ def test_decode_free_running_reference_quirks(cuda_device, weights, quirk):
     torch.testing.assert_close(img.float().cpu(), d["image_embeds"], rtol=0, atol=1e-2)
 
 
+def test_left_padded_ragged_batch_matches_reference(cuda_device, weights):
+    """tokenizer_padding_side == "left" (metamorph_arch.py:373-386) with ragged lengths: every sample sits at the END of
+    its batch row; the fused attention handles it through the segment tables (round 1 raised NotImplementedError).
+    Golden = the reference's own forward (oracle/make_golden_leftpad.py)."""
+    lp = torch.load(os.path.join(G, "leftpad_tiny.pt"), weights_only=False)
+    model = build_product_model(TINY, weights)
+    model.config.tokenizer_padding_side = "left"
+    ids, mask, labs, images = make_batch(TINY)
+    plan = model.plan_inputs(ids, mask, labs, images.shape[0])
+    assert torch.equal(plan.labels, lp["new_labels"]) and torch.equal(plan.attention_mask.bool(), lp["new_attention_mask"].bool())
+    assert torch.equal(plan.image_positions, lp["image_positions"])
+    for mode in ("eval", "train"):
+        getattr(model, mode)()
+        with torch.set_grad_enabled(mode == "train"):
+            out = model(input_ids=ids, attention_mask=mask, labels=labs, images=images.bfloat16())
+        for k in ("loss", "loss_language", "loss_image_ar"):
+            ref = float(lp["fp32"][k])
+            got = float(out.loss) if k == "loss" else getattr(model, k)
+            assert abs(got - ref) <= 1e-3 * abs(ref) + 2e-3, (mode, k, got, ref)
+        if mode == "eval":
+            err = (out.hidden_states[:, -1, :32].float().cpu() - lp["hidden_last"]).abs().max().item()
+            assert err < 5e-2, err
+        else:
+            out.loss.backward()
+            g = model.model.layers[0].self_attn.qkv_proj.weight.grad
+            assert g is not None and torch.isfinite(g).all() and float(g.abs().sum()) > 0
+
+
 def test_missing_library_or_cpu_tensor_fails_loudly(model):
     from metamorph_b200._lib import MetaMorphB200Error
     from metamorph_b200 import ops
