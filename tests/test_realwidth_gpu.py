@@ -36,10 +36,18 @@ def case(request, cuda_device):
 
 
 def _budget(ours, ref32, ref16, floor, what):
+    """The bf16 budget of tests/test_model_gpu.py AND a much tighter bound: the reference's eager bf16 run rounds after
+    every op (its logits sit ~1.1 away from its own fp32 run at this width), the fused kernels keep fp32 accumulators:
+    measured 0.05-0.06 (profiles/r02_gpu_tests.txt), asserted <= 0.25 x the bf16 reference's own error."""
     err = (ours.float().cpu() - ref32).abs().max().item()
-    bud = 1.5 * (ref16.float() - ref32).abs().max().item() + floor
-    print(f"[realwidth] {what}: |ours-fp32| = {err:.5f}  budget {bud:.5f}  (|bf16ref-fp32| = {(ref16.float() - ref32).abs().max().item():.5f})")
+    ref_err = (ref16.float() - ref32).abs().max().item()
+    bud = 1.5 * ref_err + floor
+    rel_rms = ((ours.float().cpu() - ref32).pow(2).mean().sqrt() / ref32.pow(2).mean().sqrt()).item()
+    print(f"[realwidth] {what}: |ours-fp32| = {err:.5f} (rms rel {rel_rms:.5f}, max |ref| {ref32.abs().max().item():.3f})  "
+          f"budget {bud:.5f}  (|bf16ref-fp32| = {ref_err:.5f})")
     assert err <= bud, f"{what}: |ours-fp32|={err:.5f} > budget {bud:.5f}"
+    assert err <= 0.25 * ref_err + floor, f"{what}: |ours-fp32|={err:.5f} not within a quarter of the bf16 reference's error {ref_err:.5f}"
+    assert rel_rms <= 1e-2, f"{what}: rms relative error {rel_rms:.5f}"
 
 
 def test_realwidth_index_tensors_bit_exact(case):
@@ -102,14 +110,14 @@ def test_realwidth_train_gradients(case):
         g = grads[k]
         assert tuple(g.shape) == tuple(d["shape"]), (k, g.shape, d["shape"])
         ref_norm, got_norm = float(d["norm"]), float(g.norm())
-        assert abs(got_norm - ref_norm) <= 5e-2 * ref_norm + 1e-6, (k, got_norm, ref_norm)
+        assert abs(got_norm - ref_norm) <= 3e-2 * ref_norm + 1e-6, (k, got_norm, ref_norm)
         vals = g.reshape(-1)[d["idx"]]
         scale = float(d["vals"].abs().max()) + 1e-12
         err = float((vals - d["vals"]).abs().max())
         rel = err / scale
         if rel > worst[0]:
             worst = (rel, k)
-        assert err <= 8e-2 * scale + 2e-2 * ref_norm / (g.numel() ** 0.5), (k, err, scale)
+        assert err <= 4e-2 * scale + 1e-2 * ref_norm / (g.numel() ** 0.5), (k, err, scale)   # measured worst: 1.8e-2 of the max entry
         checked += 1
     print(f"[realwidth] case {name}: {checked} gradient tensors checked, worst sampled error {worst[0]:.4f} of max entry ({worst[1]})")
     assert checked >= 17
