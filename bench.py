@@ -468,7 +468,7 @@ def main():
     achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
     traffic = None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_gemm_ncu_summary.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_gemm_ncu_summary.json")) as f:
             traffic = json.load(f).get("dram_bytes_per_launch")
     except Exception:  # noqa: BLE001
         pass

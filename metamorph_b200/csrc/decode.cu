@@ -23,6 +23,25 @@ typedef CUresult (*PFN_encodeTiledSk)(CUtensorMap*, CUtensorMapDataType, cuuint3
 
 namespace {
 
+// L2 prefetch of the NEXT kernel's weights (decode step): weights never change during a step, so the CTAs of a
+// weight-streaming kernel whose own stream is draining ask the memory system for the first megabytes of the following
+// kernel's weight matrix. The kernel boundary (drain, dependency latency, launch ramp of the next grid: 3-5 us, five times
+// per layer) then moves HBM bytes instead of idling, and the next kernel finds the head of its stream in the 126 MB L2.
+// Every CTA prefetches its own 1/gridDim slice, in <= 32 KB bulk requests (fire and forget, no completion tracking).
+__device__ __forceinline__ void l2_prefetch_share(const void* base, long long bytes) {
+  if (base == nullptr || bytes <= 0) return;
+  const long long nblk = (long long)gridDim.x * gridDim.y * gridDim.z;
+  const long long bid = ((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  long long per = ((bytes + nblk - 1) / nblk + 127) & ~127ll;
+  long long lo = bid * per, hi = lo + per;
+  if (hi > bytes) hi = bytes & ~15ll;
+  const char* p = reinterpret_cast<const char*>(base);
+  for (long long o = lo; o < hi; o += 32768) {
+    const unsigned n = (unsigned)((hi - o) < 32768 ? (hi - o) : 32768);
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p + o), "r"(n) : "memory");
+  }
+}
+
 constexpr int SK_THREADS = 256;
 enum SkEpi : int { SK_STORE = 0, SK_BIAS = 1, SK_RESID = 2, SK_BIAS_GELU = 3, SK_SWIGLU = 4 };
 
@@ -32,7 +51,7 @@ __global__ void __launch_bounds__(SK_THREADS)
 skinny_gemm_kernel(const bf16* __restrict__ x, long long ldx, const bf16* __restrict__ W,
                    long long ldw, void* __restrict__ y, long long ldy, const bf16* __restrict__ bias,
                    const bf16* __restrict__ resid, long long ldr, int m, int N, int K, int epi,
-                   int out_f32, int pdl) {
+                   int out_f32, int pdl, const void* __restrict__ pf, long long pf_bytes) {
   constexpr int G = ROWS / 16;
   __shared__ float red[SK_THREADS / 32][ROWS][8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -101,6 +120,7 @@ skinny_gemm_kernel(const bf16* __restrict__ x, long long ldx, const bf16* __rest
     }
   }
   if (pdl & 8) griddep_launch();
+  if (threadIdx.x == 0) l2_prefetch_share(pf, pf_bytes);     // own stream is done: pull the next kernel's weights
   // acc[i]: c0,c1 = (row n = i*16+g, batch 2t,2t+1); c2,c3 = (row n+8, batch 2t,2t+1)
 #pragma unroll
   for (int i = 0; i < G; ++i) {
@@ -156,7 +176,7 @@ __global__ void __launch_bounds__(SK2_THREADS)
 skinny_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const bf16* __restrict__ x, long long ldx,
                        void* __restrict__ y, long long ldy, const bf16* __restrict__ bias,
                        const bf16* __restrict__ resid, long long ldr, int m, int N, int K, int epi, int out_f32,
-                       int pdl) {
+                       int pdl, const void* __restrict__ pf, long long pf_bytes) {
   constexpr int G = ROWS >= 16 ? ROWS / 16 : 1;
   constexpr bool HALF = ROWS == 8;             // 8-row slab: rows 8..15 of the MMA operand are zero
   constexpr int BOX = ROWS * 128;              // bytes of one [ROWS x 64 k] TMA box
@@ -191,6 +211,7 @@ skinny_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const bf16* _
         for (int bx = 0; bx < 4; ++bx)
           tma_load_2d(base + s * STAGE + bx * BOX, &tmap_w, bar + 8 * s, kt * SK2_KT + bx * 64, n0);
       }
+      l2_prefetch_share(pf, pf_bytes);       // this CTA's weight stream is fully requested: start on the next kernel's
     }
   } else {
     const int cw = warp - 1;                 // consumer index 0..3
@@ -307,7 +328,8 @@ __global__ void __launch_bounds__(DA_THREADS)
 decode_attn_kernel(const bf16* __restrict__ qkv, long long ldqkv, bf16* __restrict__ kc,
                    bf16* __restrict__ vc, const int* __restrict__ pos_arr,
                    const float* __restrict__ cos_t, const float* __restrict__ sin_t,
-                   float* __restrict__ part, int Hq, int Hkv, int Tmax, int S, float scale) {
+                   float* __restrict__ part, int Hq, int Hkv, int Tmax, int S, float scale,
+                   const void* __restrict__ pf, long long pf_bytes) {
   extern __shared__ float sm[];
   float* sq = sm;                          // [G][128] rotated, scaled q
   float* sknew = sq + G * DA_D;            // [128] rotated new k
@@ -316,6 +338,7 @@ decode_attn_kernel(const bf16* __restrict__ qkv, long long ldqkv, bf16* __restri
   float* sscore = sred + 8 * G * DA_D;     // [G][chunk_pad]
   const int hk = blockIdx.x, b = blockIdx.y, sp = blockIdx.z;
   griddep_launch();
+  if (threadIdx.x == 0) l2_prefetch_share(pf, pf_bytes);   // attention barely touches HBM: stream the MLP weights meanwhile
   griddep_wait();
   const int pos = pos_arr[b];
   const int n_ctx = pos + 1;
@@ -604,9 +627,10 @@ __global__ void decode_select_hidden_kernel(const int* __restrict__ mode, const 
 
 }  // namespace
 
-MM_API int mm_skinny_gemm(const void* x, const void* W, void* y, const void* bias, const void* resid,
-                          long long ldx, long long ldw, long long ldy, long long ldr, int m, int N,
-                          int K, int epilogue, int out_f32, cudaStream_t stream) {
+MM_API int mm_skinny_gemm_pf(const void* x, const void* W, void* y, const void* bias, const void* resid,
+                             long long ldx, long long ldw, long long ldy, long long ldr, int m, int N,
+                             int K, int epilogue, int out_f32, const void* prefetch, long long prefetch_bytes,
+                             cudaStream_t stream) {
   MM_CHECK_ARG(m >= 1 && m <= 8, "mm_skinny_gemm: batch must be in [1,8] (m=%d)", m);
   MM_CHECK_ARG(K % 32 == 0 && ldx % 8 == 0 && ldw % 8 == 0, "mm_skinny_gemm: need K%%32==0, ldx/ldw%%8==0");
   MM_CHECK_ARG(epilogue >= SK_STORE && epilogue <= SK_SWIGLU, "mm_skinny_gemm: bad epilogue");
@@ -657,7 +681,7 @@ MM_API int mm_skinny_gemm(const void* x, const void* W, void* y, const void* bia
       MM_CHECK_CUDA(e32);
       MM_CHECK_CUDA(launch_pdl(pm & 1, skinny_gemm_tma_kernel<32>, dim3((N + 31) / 32), dim3(SK2_THREADS), smem, stream, tm,
                                (const bf16*)x, ldx, y, ldy, (const bf16*)bias, (const bf16*)resid, ldr, m, N, K,
-                               epilogue, out_f32, pm));
+                               epilogue, out_f32, pm, prefetch, prefetch_bytes));
     } else if (rows == 8) {
       static std::once_flag o8;
       static cudaError_t e8 = cudaSuccess;
@@ -667,7 +691,7 @@ MM_API int mm_skinny_gemm(const void* x, const void* W, void* y, const void* bia
       MM_CHECK_CUDA(e8);
       MM_CHECK_CUDA(launch_pdl(pm & 1, skinny_gemm_tma_kernel<8>, dim3((N + 7) / 8), dim3(SK2_THREADS), smem, stream, tm,
                                (const bf16*)x, ldx, y, ldy, (const bf16*)bias, (const bf16*)resid, ldr, m, N, K,
-                               epilogue, out_f32, pm));
+                               epilogue, out_f32, pm, prefetch, prefetch_bytes));
     } else {
       static std::once_flag o16;
       static cudaError_t e16 = cudaSuccess;
@@ -677,7 +701,7 @@ MM_API int mm_skinny_gemm(const void* x, const void* W, void* y, const void* bia
       MM_CHECK_CUDA(e16);
       MM_CHECK_CUDA(launch_pdl(pm & 1, skinny_gemm_tma_kernel<16>, dim3((N + 15) / 16), dim3(SK2_THREADS), smem, stream, tm,
                                (const bf16*)x, ldx, y, ldy, (const bf16*)bias, (const bf16*)resid, ldr, m, N, K,
-                               epilogue, out_f32, pm));
+                               epilogue, out_f32, pm, prefetch, prefetch_bytes));
     }
     MM_CHECK_LAUNCH();
     return MM_OK;
@@ -685,23 +709,30 @@ MM_API int mm_skinny_gemm(const void* x, const void* W, void* y, const void* bia
   if (rows32)
     MM_CHECK_CUDA(launch_pdl(pm & 1, skinny_gemm_kernel<32>, dim3((N + 31) / 32), dim3(SK_THREADS), 0, stream, (const bf16*)x,
                              ldx, (const bf16*)W, ldw, y, ldy, (const bf16*)bias, (const bf16*)resid, ldr, m, N, K,
-                             epilogue, out_f32, pm));
+                             epilogue, out_f32, pm, prefetch, prefetch_bytes));
   else
     MM_CHECK_CUDA(launch_pdl(pm & 1, skinny_gemm_kernel<16>, dim3((N + 15) / 16), dim3(SK_THREADS), 0, stream, (const bf16*)x,
                              ldx, (const bf16*)W, ldw, y, ldy, (const bf16*)bias, (const bf16*)resid, ldr, m, N, K,
-                             epilogue, out_f32, pm));
+                             epilogue, out_f32, pm, prefetch, prefetch_bytes));
   MM_CHECK_LAUNCH();
   return MM_OK;
+}
+
+MM_API int mm_skinny_gemm(const void* x, const void* W, void* y, const void* bias, const void* resid,
+                          long long ldx, long long ldw, long long ldy, long long ldr, int m, int N,
+                          int K, int epilogue, int out_f32, cudaStream_t stream) {
+  return mm_skinny_gemm_pf(x, W, y, bias, resid, ldx, ldw, ldy, ldr, m, N, K, epilogue, out_f32, nullptr, 0, stream);
 }
 
 MM_API long long mm_decode_attn_workspace_bytes(int B, int Hq, int Hkv, int splits) {
   return (long long)B * Hkv * splits * (Hq / Hkv) * (2 + DA_D) * 4;
 }
 
-MM_API int mm_decode_attn(const void* qkv, long long ldqkv, void* kcache, void* vcache, const int* pos,
-                          const float* cos_t, const float* sin_t, void* out, long long ldo, int B,
-                          int Hq, int Hkv, int head_dim, int Tmax, float scale, void* workspace,
-                          long long workspace_bytes, int splits, cudaStream_t stream) {
+MM_API int mm_decode_attn_pf(const void* qkv, long long ldqkv, void* kcache, void* vcache, const int* pos,
+                             const float* cos_t, const float* sin_t, void* out, long long ldo, int B,
+                             int Hq, int Hkv, int head_dim, int Tmax, float scale, void* workspace,
+                             long long workspace_bytes, int splits, const void* prefetch, long long prefetch_bytes,
+                             cudaStream_t stream) {
   MM_CHECK_ARG(head_dim == DA_D && Hq % Hkv == 0, "mm_decode_attn: need head_dim 128");
   const int G = Hq / Hkv;
   MM_CHECK_ARG(G == 1 || G == 2 || G == 4 || G == 8, "mm_decode_attn: GQA group must be 1, 2, 4 or 8");
@@ -719,7 +750,7 @@ MM_API int mm_decode_attn(const void* qkv, long long ldqkv, void* kcache, void* 
                                          (int)smem));                                                        \
     MM_CHECK_CUDA(launch_pdl(mm_pdl_mode() & 2, decode_attn_kernel<GG>, grid, dim3(DA_THREADS), smem, stream, (const bf16*)qkv,  \
                              ldqkv, (bf16*)kcache, (bf16*)vcache, pos, cos_t, sin_t, (float*)workspace, Hq,   \
-                             Hkv, Tmax, splits, scale));                                                     \
+                             Hkv, Tmax, splits, scale, prefetch, prefetch_bytes));                           \
   } while (0)
   if (G == 1) MM_DA_LAUNCH(1);
   else if (G == 2) MM_DA_LAUNCH(2);
@@ -731,6 +762,14 @@ MM_API int mm_decode_attn(const void* qkv, long long ldqkv, void* kcache, void* 
                            (bf16*)out, ldo, Hkv, G, splits));
   MM_CHECK_LAUNCH();
   return MM_OK;
+}
+
+MM_API int mm_decode_attn(const void* qkv, long long ldqkv, void* kcache, void* vcache, const int* pos,
+                          const float* cos_t, const float* sin_t, void* out, long long ldo, int B,
+                          int Hq, int Hkv, int head_dim, int Tmax, float scale, void* workspace,
+                          long long workspace_bytes, int splits, cudaStream_t stream) {
+  return mm_decode_attn_pf(qkv, ldqkv, kcache, vcache, pos, cos_t, sin_t, out, ldo, B, Hq, Hkv, head_dim, Tmax, scale,
+                           workspace, workspace_bytes, splits, nullptr, 0, stream);
 }
 
 MM_API int mm_kv_prefill(const void* qkv, long long ld, void* kcache, void* vcache, int B, int T, int Hq,

@@ -50,6 +50,7 @@ struct EpiParams {
   int out_f32;     // 1: C is fp32, 0: bf16
   int accumulate;  // 1: C += result (C read in its own dtype)
   float alpha;     // result scale applied to acc before everything else
+  int tma_store;   // 1: bf16 result leaves through shared memory + cp.async.bulk.tensor stores (2-CTA kernel)
 };
 
 template <int BN>
@@ -243,6 +244,58 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, float (&v)[3
       }
     }
 }
+// The store-free part of the plain epilogues (STORE / BIAS / BIAS_GELU_* / RESID / BIAS_RESID, bf16 out, no accumulate):
+// v -> bias -> activation -> residual, packed to 16 bf16x2 words (the TMA-store path writes them to shared memory).
+__device__ __forceinline__ void epilogue_pack_chunk(const EpiParams& ep, float (&v)[32], int row, bool row_ok, int col0,
+                                                    int N, uint32_t (&out)[16]) {
+  const bool full_chunk = (col0 + 32 <= N);
+  if (ep.epi == EPI_BIAS || ep.epi == EPI_BIAS_GELU_ERF || ep.epi == EPI_BIAS_GELU_TANH || ep.epi == EPI_BIAS_RESID) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (full_chunk || col0 + j < N) v[j] += __bfloat162float(__ldg(ep.bias + col0 + j));
+  }
+  if (ep.epi == EPI_BIAS_GELU_ERF) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+  } else if (ep.epi == EPI_BIAS_GELU_TANH) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
+  }
+  if (row_ok && (ep.epi == EPI_RESID || ep.epi == EPI_BIAS_RESID)) {
+    const bf16* rp = ep.resid + (long long)row * ep.ldr + col0;
+    if (full_chunk) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        const int4 rr = *reinterpret_cast<const int4*>(rp + j);
+        float2 f;
+        f = unpack_bf16x2(rr.x); v[j] += f.x; v[j + 1] += f.y;
+        f = unpack_bf16x2(rr.y); v[j + 2] += f.x; v[j + 3] += f.y;
+        f = unpack_bf16x2(rr.z); v[j + 4] += f.x; v[j + 5] += f.y;
+        f = unpack_bf16x2(rr.w); v[j + 6] += f.x; v[j + 7] += f.y;
+      }
+    } else {
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < N) v[j] += __bfloat162float(rp[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) out[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+}
+
+// 2-D tiled store shared -> global (the tensor map clips rows / columns past the matrix)
+__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t smem_src, int32_t c_inner, int32_t c_outer) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(smem_src), "r"(c_inner), "r"(c_outer)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
@@ -509,7 +562,8 @@ constexpr int kStages2 = 6;
 constexpr int kA2Bytes = BM * BK * 2;          // this CTA's 128 rows of A
 constexpr int kB2Bytes = (BN2 / 2) * BK * 2;   // this CTA's 128 columns of B
 constexpr int kStage2Bytes = kA2Bytes + kB2Bytes;
-constexpr int kSmem2Bytes = kStages2 * kStage2Bytes + 1024 + 384;   // + alignment slack + barriers / CLC responses
+constexpr int kCStageBytes = 128 * 64 * 2;   // one [128 rows x 64 cols] bf16 staging tile of the TMA-store epilogue
+constexpr int kSmem2Bytes = kStages2 * kStage2Bytes + 2 * kCStageBytes + 1024 + 384;   // + alignment slack + barriers / CLC responses
 
 // Tile schedule. DYN = false: static persistent (cluster c computes tiles c, c + #clusters, ...). DYN = true (default):
 // the grid holds ONE cluster per tile and every resident cluster keeps stealing not-yet-launched clusters through
@@ -518,11 +572,12 @@ constexpr int kSmem2Bytes = kStages2 * kStage2Bytes + 1024 + 384;   // + alignme
 template <bool A_MN, bool B_MN, bool DYN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                         const __grid_constant__ CUtensorMap tmap_b, int M, int N, int K, int group_m, int l2_hint,
-                         EpiParams ep) {
+                         const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_c,
+                         int M, int N, int K, int group_m, int l2_hint, EpiParams ep) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + kStages2 * kStage2Bytes;
+  const uint32_t cstage_base = smem_base + kStages2 * kStage2Bytes;      // 1024-aligned: 128-byte swizzle atoms
+  const uint32_t bar_base = cstage_base + 2 * kCStageBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages2 + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages2 + a); };
@@ -545,6 +600,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
+    if (ep.tma_store) prefetch_tmap(&tmap_c);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages2; ++s) {
@@ -713,6 +769,51 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN2;
+      if (ep.tma_store) {
+        // TMA-store epilogue: 64 columns at a time go through a 128-byte-swizzled [128 x 64] staging tile (two of them,
+        // so the store of one overlaps the math of the next) and leave as ONE bulk tensor store per CTA — full 128-byte
+        // lines instead of 32 x 64-byte row fragments per warp; the tensor map clips the M / N tails.
+        uint8_t* cstage = smem_raw + (cstage_base - smem_u32(smem_raw));
+        const int rloc = q * 32 + lane;
+        const bool issuer = (warp == 4 && lane == 0);
+#pragma unroll 1
+        for (int pr = 0; pr < BN2 / 64; ++pr) {
+          const int colp = n0 + pr * 64;
+          if (colp >= N) break;                 // CTA-uniform
+          const int buf = pr & 1;
+          if (issuer) tma_store_wait_read<1>();  // the store issued two pairs ago has finished reading this buffer
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const int col0 = colp + h2 * 32;
+            uint32_t r[32];
+            __syncwarp();
+            tmem_ld_32x32b_x32(taddr + (pr * 2 + h2) * 32, r);
+            tmem_ld_wait();
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * ep.alpha;
+            uint32_t o[16];
+            if (col0 < N) {
+              epilogue_pack_chunk(ep, v, row, row_ok, col0, N, o);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) o[j] = 0u;
+            }
+            uint8_t* dst = cstage + buf * kCStageBytes + rloc * 128;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<int4*>(dst + (((h2 * 4 + j) ^ (rloc & 7)) << 4)) =
+                  make_int4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+          }
+          fence_proxy_async_smem();              // generic-proxy writes -> visible to the TMA engine
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (issuer) {
+            tma_store_2d(&tmap_c, cstage_base + buf * kCStageBytes, colp, m_blk * 2 * BM + (int)rank * BM);
+            tma_store_commit();
+          }
+        }
+      } else {
 #pragma unroll 1
       for (int c = 0; c < BN2 / 32; ++c) {
         const int col0 = n0 + c * 32;
@@ -726,6 +827,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * ep.alpha;
         epilogue_chunk(ep, v, row, row_ok, col0, N);
       }
+      }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -736,6 +838,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   }
 
+  if (ep.tma_store && warp == 4 && lane == 0) tma_store_wait_all();   // the staging tiles must outlive their stores
   tcgen05_fence_before();
   cluster_sync_all();   // nobody may exit (or free TMEM) while the peer can still touch its smem / barriers
   if (warp == 2) {
@@ -798,8 +901,14 @@ int env_dynamic_tiles() {   // MM_GEMM_DYNAMIC=0 selects the static persistent s
   static const int v = [] { const char* e = getenv("MM_GEMM_DYNAMIC"); return e ? atoi(e) : 1; }();
   return v;
 }
-int env_l2_hint() {   // MM_GEMM_L2HINT=0 disables the TMA L2 eviction hints of the 2-CTA kernel
-  static const int v = [] { const char* e = getenv("MM_GEMM_L2HINT"); return e ? atoi(e) : 1; }();
+int env_tma_store() {   // MM_GEMM_TMA_STORE=0: direct st.global epilogue everywhere (A/B measurements)
+  static const int v = [] { const char* e = getenv("MM_GEMM_TMA_STORE"); return e ? atoi(e) : 1; }();
+  return v;
+}
+int env_l2_hint() {   // MM_GEMM_L2HINT=1 enables the TMA L2 eviction hints of the 2-CTA kernel. OFF by default: measured on B200
+  // (profiles/r02_gemm_ab.txt) they are neutral on the forward / dgrad shapes and cost 14-15 % on the wgrad
+  // ([28672 x 4096] = A^T B over 16384 tokens: 1323 vs 1542 TFLOP/s) and qkv (1276 vs 1503) shapes.
+  static const int v = [] { const char* e = getenv("MM_GEMM_L2HINT"); return e ? atoi(e) : 0; }();
   return v;
 }
 
@@ -831,7 +940,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, co
 }
 
 template <bool A_MN, bool B_MN, bool DYN>
-int launch2(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EpiParams& ep,
+int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int M, int N, int K, const EpiParams& ep,
             cudaStream_t stream) {
   auto kern = gemm_tcgen05_2cta_kernel<A_MN, B_MN, DYN>;
   static std::once_flag once;
@@ -848,7 +957,7 @@ int launch2(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, c
   if (gm < 8) gm = 8;
   if (gm > 32) gm = 32;
   if (env_group_m() > 0) gm = env_group_m();   // rasterisation experiments (MM_GEMM_GM, read once)
-  kern<<<2 * clusters, kThreads, kSmem2Bytes, stream>>>(ta, tb, M, N, K, (int)gm, env_l2_hint(), ep);
+  kern<<<2 * clusters, kThreads, kSmem2Bytes, stream>>>(ta, tb, tc, M, N, K, (int)gm, env_l2_hint(), ep);
   MM_CHECK_LAUNCH();
   return MM_OK;
 }
@@ -910,14 +1019,20 @@ MM_API int mm_gemm_bf16(const void* A, const void* B, void* C, const void* bias,
     ep2.resid = reinterpret_cast<const bf16*>(resid); ep2.ldr = ldr;
     ep2.aux = reinterpret_cast<bf16*>(aux); ep2.ld_aux = ld_aux;
     ep2.epi = epilogue; ep2.out_f32 = out_f32; ep2.accumulate = accumulate; ep2.alpha = alpha;
-    if (env_dynamic_tiles()) {
-      if (!a_mn_major && !b_mn_major) return launch2<false, false, true>(ta2, tb2, (int)M, (int)N, (int)K, ep2, stream);
-      if (!a_mn_major && b_mn_major) return launch2<false, true, true>(ta2, tb2, (int)M, (int)N, (int)K, ep2, stream);
-      return launch2<true, true, true>(ta2, tb2, (int)M, (int)N, (int)K, ep2, stream);
+    // plain bf16 results (forward projections, dgrads, non-accumulating wgrads) leave through the TMA-store epilogue
+    ep2.tma_store = (env_tma_store() && !out_f32 && !accumulate && epilogue != EPI_SWIGLU && epilogue != EPI_SWIGLU_BWD) ? 1 : 0;
+    CUtensorMap tc2 = ta2;    // placeholder when unused (never dereferenced)
+    if (ep2.tma_store) {
+      if ((rc2 = make_tmap(&tc2, C, N, M, ldc, 64, BM))) return rc2;
     }
-    if (!a_mn_major && !b_mn_major) return launch2<false, false, false>(ta2, tb2, (int)M, (int)N, (int)K, ep2, stream);
-    if (!a_mn_major && b_mn_major) return launch2<false, true, false>(ta2, tb2, (int)M, (int)N, (int)K, ep2, stream);
-    return launch2<true, true, false>(ta2, tb2, (int)M, (int)N, (int)K, ep2, stream);
+    if (env_dynamic_tiles()) {
+      if (!a_mn_major && !b_mn_major) return launch2<false, false, true>(ta2, tb2, tc2, (int)M, (int)N, (int)K, ep2, stream);
+      if (!a_mn_major && b_mn_major) return launch2<false, true, true>(ta2, tb2, tc2, (int)M, (int)N, (int)K, ep2, stream);
+      return launch2<true, true, true>(ta2, tb2, tc2, (int)M, (int)N, (int)K, ep2, stream);
+    }
+    if (!a_mn_major && !b_mn_major) return launch2<false, false, false>(ta2, tb2, tc2, (int)M, (int)N, (int)K, ep2, stream);
+    if (!a_mn_major && b_mn_major) return launch2<false, true, false>(ta2, tb2, tc2, (int)M, (int)N, (int)K, ep2, stream);
+    return launch2<true, true, false>(ta2, tb2, tc2, (int)M, (int)N, (int)K, ep2, stream);
   }
   int bn = 256;
   if (force_bn == 128 || force_bn == 256) {
@@ -942,6 +1057,7 @@ MM_API int mm_gemm_bf16(const void* A, const void* B, void* C, const void* bias,
   ep.resid = reinterpret_cast<const bf16*>(resid); ep.ldr = ldr;
   ep.aux = reinterpret_cast<bf16*>(aux); ep.ld_aux = ld_aux;
   ep.epi = epilogue; ep.out_f32 = out_f32; ep.accumulate = accumulate; ep.alpha = alpha;
+  ep.tma_store = 0;
 
   const int m = (int)M, n = (int)N, k = (int)K;
   if (bn == 256) {

@@ -15,7 +15,7 @@ shapes = [("fwd gate/up  [M,4096]x[28672,4096]^T", (M, 28672, 4096), False, Fals
           ("dgrad gate/up [M,28672]x[28672,4096]", (M, 4096, 28672), False, True),
           ("wgrad gate/up [M,28672]^T x [M,4096]", (28672, 4096, M), True, True),
           ("fwd qkv      [M,4096]x[6144,4096]^T", (M, 6144, 4096), False, False)]
-tag = f"dynamic={os.environ.get('MM_GEMM_DYNAMIC', '1')} l2hint={os.environ.get('MM_GEMM_L2HINT', '1')}"
+tag = f"dynamic={os.environ.get('MM_GEMM_DYNAMIC', '1')} l2hint={os.environ.get('MM_GEMM_L2HINT', '0')}"
 for name, (m, n, k), a_mn, b_mn in shapes:
     a = (torch.randn((k, m) if a_mn else (m, k), device="cuda") * 0.1).bfloat16()
     b = (torch.randn((k, n) if b_mn else (n, k), device="cuda") * 0.1).bfloat16()

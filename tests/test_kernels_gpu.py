@@ -39,7 +39,8 @@ def test_gemm_layouts(cuda_device, a_mn, b_mn, shape):
         _close(out, ref, 1e-2, f"gemm bn={bn}")
 
 
-def test_gemm_epilogues(cuda_device):
+@pytest.mark.parametrize("force_bn", [0, 512])      # 512 = the 2-CTA kernel (TMA-store epilogue for plain bf16 results)
+def test_gemm_epilogues(cuda_device, force_bn):
     from metamorph_b200 import ops
     torch.manual_seed(1)
     M, N, K = 520, 1160, 320
@@ -48,22 +49,30 @@ def test_gemm_epilogues(cuda_device):
     bias = torch.randn(N, device=cuda_device).bfloat16()
     res = torch.randn(M, N, device=cuda_device).bfloat16()
     base = a.float() @ w.float().t()
-    _close(ops.gemm(a, w, bias=bias, epilogue=ops.EPI_BIAS), base + bias.float(), 1e-2, "bias")
-    _close(ops.gemm(a, w, bias=bias, epilogue=ops.EPI_BIAS_GELU_ERF), F.gelu(base + bias.float()), 1e-2, "gelu_erf")
-    _close(ops.gemm(a, w, bias=bias, epilogue=ops.EPI_BIAS_GELU_TANH),
+    kw = dict(force_bn=force_bn)
+    _close(ops.gemm(a, w, **kw), base, 1e-2, "store")
+    _close(ops.gemm(a, w, alpha=0.5, **kw), 0.5 * base, 1e-2, "alpha")
+    _close(ops.gemm(a, w, bias=bias, epilogue=ops.EPI_BIAS, **kw), base + bias.float(), 1e-2, "bias")
+    _close(ops.gemm(a, w, bias=bias, epilogue=ops.EPI_BIAS_GELU_ERF, **kw), F.gelu(base + bias.float()), 1e-2, "gelu_erf")
+    _close(ops.gemm(a, w, bias=bias, epilogue=ops.EPI_BIAS_GELU_TANH, **kw),
            F.gelu(base + bias.float(), approximate="tanh"), 1e-2, "gelu_tanh")
-    _close(ops.gemm(a, w, resid=res, epilogue=ops.EPI_RESID), base + res.float(), 1e-2, "resid")
-    _close(ops.gemm(a, w, bias=bias, resid=res, epilogue=ops.EPI_BIAS_RESID), base + bias.float() + res.float(), 1e-2, "bias_resid")
+    _close(ops.gemm(a, w, resid=res, epilogue=ops.EPI_RESID, **kw), base + res.float(), 1e-2, "resid")
+    _close(ops.gemm(a, w, bias=bias, resid=res, epilogue=ops.EPI_BIAS_RESID, **kw), base + bias.float() + res.float(), 1e-2, "bias_resid")
     # in-place residual (C aliases R)
     r2 = res.clone()
-    ops.gemm(a, w, resid=r2, out=r2, epilogue=ops.EPI_RESID)
+    ops.gemm(a, w, resid=r2, out=r2, epilogue=ops.EPI_RESID, **kw)
     _close(r2, base + res.float(), 1e-2, "resid in place")
+    # a column slice of a wider buffer as the output (pitch != N): the store must respect ldc and leave the rest alone
+    wide = torch.full((M, N + 72), 5.0, device=cuda_device, dtype=torch.bfloat16)
+    ops.gemm(a, w, out=wide[:, 8:8 + N], **kw)
+    _close(wide[:, 8:8 + N], base, 1e-2, "strided out")
+    assert torch.all(wide[:, :8].float() == 5.0) and torch.all(wide[:, 8 + N:].float() == 5.0)
     # fp32 output + accumulate
     c32 = torch.ones(M, N, device=cuda_device, dtype=torch.float32)
-    ops.gemm(a, w, out=c32, out_dtype=torch.float32, accumulate=True)
+    ops.gemm(a, w, out=c32, out_dtype=torch.float32, accumulate=True, **kw)
     _close(c32, base + 1.0, 1e-3, "f32 accumulate")
     c16 = res.clone()
-    ops.gemm(a, w, out=c16, accumulate=True)
+    ops.gemm(a, w, out=c16, accumulate=True, **kw)
     _close(c16, base + res.float(), 1e-2, "bf16 accumulate")
     # swiglu: columns interleaved in chunks of [16 gate | 16 up]
     N2 = 1152
