@@ -152,17 +152,7 @@ long long mm_decode_attn_workspace_bytes(int B, int Hq, int Hkv, int splits);
 int mm_decode_attn(const void* qkv, long long ldqkv, void* kcache, void* vcache, const int* pos,
                    const float* cos_t, const float* sin_t, void* out, long long ldo, int B, int Hq, int Hkv,
                    int head_dim, int Tmax, float scale, void* workspace, long long workspace_bytes, int splits,
-                   cudaStream_t s);/* Same two kernels with an L2 prefetch hint for the decode step: while its own weight stream drains (skinny GEMM) or
- * while attention leaves HBM idle, every CTA requests its 1/grid share of [prefetch, prefetch + prefetch_bytes) — the head
- * of the NEXT kernel's weight matrix — into L2, so the 3-5 us kernel boundaries of the dependency chain move HBM bytes. */
-int mm_skinny_gemm_pf(const void* x, const void* W, void* y, const void* bias, const void* resid, long long ldx,
-                      long long ldw, long long ldy, long long ldr, int m, int N, int K, int epilogue, int out_f32,
-                      const void* prefetch, long long prefetch_bytes, cudaStream_t s);
-int mm_decode_attn_pf(const void* qkv, long long ldqkv, void* kcache, void* vcache, const int* pos, const float* cos_t,
-                      const float* sin_t, void* out, long long ldo, int B, int Hq, int Hkv, int head_dim, int Tmax,
-                      float scale, void* workspace, long long workspace_bytes, int splits, const void* prefetch,
-                      long long prefetch_bytes, cudaStream_t s);
-
+                   cudaStream_t s);
 int mm_kv_prefill(const void* qkv, long long ld, void* kcache, void* vcache, int B, int T, int Hq, int Hkv,
                   int head_dim, int Tmax, cudaStream_t s);
 int mm_decode_state_step(int* in_image_mode, int* total_image_tokens, int* total_output, int* finished, int* pos,

@@ -23,143 +23,7 @@ typedef CUresult (*PFN_encodeTiledSk)(CUtensorMap*, CUtensorMapDataType, cuuint3
 
 namespace {
 
-// L2 prefetch of the NEXT kernel's weights (decode step): weights never change during a step, so the CTAs of a
-// weight-streaming kernel whose own stream is draining ask the memory system for the first megabytes of the following
-// kernel's weight matrix. The kernel boundary (drain, dependency latency, launch ramp of the next grid: 3-5 us, five times
-// per layer) then moves HBM bytes instead of idling, and the next kernel finds the head of its stream in the 126 MB L2.
-// Every CTA prefetches its own 1/gridDim slice, in <= 32 KB bulk requests (fire and forget, no completion tracking).
-__device__ __forceinline__ void l2_prefetch_share(const void* base, long long bytes) {
-  if (base == nullptr || bytes <= 0) return;
-  const long long nblk = (long long)gridDim.x * gridDim.y * gridDim.z;
-  const long long bid = ((long long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-  long long per = ((bytes + nblk - 1) / nblk + 127) & ~127ll;
-  long long lo = bid * per, hi = lo + per;
-  if (hi > bytes) hi = bytes & ~15ll;
-  const char* p = reinterpret_cast<const char*>(base);
-  for (long long o = lo; o < hi; o += 32768) {
-    const unsigned n = (unsigned)((hi - o) < 32768 ? (hi - o) : 32768);
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p + o), "r"(n) : "memory");
-  }
-}
-
-constexpr int SK_THREADS = 256;
 enum SkEpi : int { SK_STORE = 0, SK_BIAS = 1, SK_RESID = 2, SK_BIAS_GELU = 3, SK_SWIGLU = 4 };
-
-// ROWS = 16 or 32 weight rows per CTA. x: [8, K] bf16 (rows >= m are ignored via m mask on store).
-template <int ROWS>
-__global__ void __launch_bounds__(SK_THREADS)
-skinny_gemm_kernel(const bf16* __restrict__ x, long long ldx, const bf16* __restrict__ W,
-                   long long ldw, void* __restrict__ y, long long ldy, const bf16* __restrict__ bias,
-                   const bf16* __restrict__ resid, long long ldr, int m, int N, int K, int epi,
-                   int out_f32, int pdl, const void* __restrict__ pf, long long pf_bytes) {
-  constexpr int G = ROWS / 16;
-  __shared__ float red[SK_THREADS / 32][ROWS][8];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = lane >> 2, t = lane & 3;
-  const int n0 = blockIdx.x * ROWS;
-  float acc[G][4];
-#pragma unroll
-  for (int i = 0; i < G; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-
-  const bf16* xrow = x + (long long)g * ldx;  // batch row g (B operand column)
-  const bool xok = g < m;
-  const int nchunks = K >> 5;
-  if (!(pdl & 8)) griddep_launch();
-  if (pdl & 4) {  // PDL prologue: weights are never written by a kernel, so pull this lane's first chunks towards L2 while the
-     // producer of x is still running
-    constexpr int UNR0 = (G == 1) ? 4 : 2;
-#pragma unroll
-    for (int u = 0; u < UNR0; ++u) {
-      const int cc = warp + u * (SK_THREADS / 32);
-      if (cc < nchunks) {
-#pragma unroll
-        for (int i = 0; i < G; ++i) {
-          const int r0 = n0 + i * 16 + g, r1 = r0 + 8;
-          if (r0 < N) prefetch_l2(W + (long long)r0 * ldw + cc * 32 + t * 8);
-          if (r1 < N) prefetch_l2(W + (long long)r1 * ldw + cc * 32 + t * 8);
-        }
-      }
-    }
-  }
-  griddep_wait();
-  // warp w handles k32-chunks w, w+8, ...; unrolled by UNR so that each lane keeps 2*G*UNR independent
-  // 128-bit weight loads in flight (the kernel is a pure HBM stream: bytes in flight per SM set its rate)
-  constexpr int UNR = (G == 1) ? 4 : 2;
-  constexpr int NW = SK_THREADS / 32;
-  for (int c = warp; c < nchunks; c += UNR * NW) {
-    int4 wa[UNR][G][2];
-    int4 xb[UNR];
-#pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      const int cc = c + u * NW;
-      const bool ok = cc < nchunks;
-      const int k0 = cc * 32 + t * 8;
-#pragma unroll
-      for (int i = 0; i < G; ++i) {
-        const int r0 = n0 + i * 16 + g, r1 = r0 + 8;
-        wa[u][i][0] = (ok && r0 < N) ? ld_nc_int4(W + (long long)r0 * ldw + k0) : make_int4(0, 0, 0, 0);
-        wa[u][i][1] = (ok && r1 < N) ? ld_nc_int4(W + (long long)r1 * ldw + k0) : make_int4(0, 0, 0, 0);
-      }
-      xb[u] = (ok && xok) ? *reinterpret_cast<const int4*>(xrow + k0) : make_int4(0, 0, 0, 0);
-    }
-#pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-#pragma unroll
-      for (int i = 0; i < G; ++i) {
-        // k-permutation: lane t owns k = 8t..8t+7 of the chunk; MMA #1 uses elements {0,1 | 2,3},
-        // MMA #2 uses {4,5 | 6,7}; the B fragment uses the same slots, so the sum is unchanged.
-        const uint32_t a1[4] = {(uint32_t)wa[u][i][0].x, (uint32_t)wa[u][i][1].x,
-                                (uint32_t)wa[u][i][0].y, (uint32_t)wa[u][i][1].y};
-        const uint32_t a2[4] = {(uint32_t)wa[u][i][0].z, (uint32_t)wa[u][i][1].z,
-                                (uint32_t)wa[u][i][0].w, (uint32_t)wa[u][i][1].w};
-        mma_bf16_16816(acc[i], a1, (uint32_t)xb[u].x, (uint32_t)xb[u].y);
-        mma_bf16_16816(acc[i], a2, (uint32_t)xb[u].z, (uint32_t)xb[u].w);
-      }
-    }
-  }
-  if (pdl & 8) griddep_launch();
-  if (threadIdx.x == 0) l2_prefetch_share(pf, pf_bytes);     // own stream is done: pull the next kernel's weights
-  // acc[i]: c0,c1 = (row n = i*16+g, batch 2t,2t+1); c2,c3 = (row n+8, batch 2t,2t+1)
-#pragma unroll
-  for (int i = 0; i < G; ++i) {
-    red[warp][i * 16 + g][2 * t] = acc[i][0];
-    red[warp][i * 16 + g][2 * t + 1] = acc[i][1];
-    red[warp][i * 16 + g + 8][2 * t] = acc[i][2];
-    red[warp][i * 16 + g + 8][2 * t + 1] = acc[i][3];
-  }
-  __syncthreads();
-  if (epi == SK_SWIGLU) {
-    // ROWS == 32: rows [0,16) gate, [16,32) up of the same 16 intermediate channels
-    if (ROWS == 32 && threadIdx.x < 128) {
-      const int r = threadIdx.x >> 3, b = threadIdx.x & 7;
-      float gsum = 0.f, usum = 0.f;
-#pragma unroll
-      for (int w = 0; w < SK_THREADS / 32; ++w) {
-        gsum += red[w][r][b];
-        usum += red[w][r + 16][b];
-      }
-      const int col = (n0 >> 1) + r;
-      if (b < m && n0 + r < N)
-        reinterpret_cast<bf16*>(y)[(long long)b * ldy + col] = __float2bfloat16(silu(gsum) * usum);
-    }
-    return;
-  }
-  for (int idx = threadIdx.x; idx < ROWS * 8; idx += SK_THREADS) {
-    const int r = idx >> 3, b = idx & 7;
-    const int n = n0 + r;
-    if (b >= m || n >= N) continue;
-    float s = 0.f;
-#pragma unroll
-    for (int w = 0; w < SK_THREADS / 32; ++w) s += red[w][r][b];
-    if (epi == SK_BIAS || epi == SK_BIAS_GELU) s += __bfloat162float(bias[n]);
-    if (epi == SK_BIAS_GELU) s = gelu_erf(s);
-    if (epi == SK_RESID) s += __bfloat162float(resid[(long long)b * ldr + n]);
-    if (out_f32) reinterpret_cast<float*>(y)[(long long)b * ldy + n] = s;
-    else reinterpret_cast<bf16*>(y)[(long long)b * ldy + n] = __float2bfloat16(s);
-  }
-}
 
 // ---------------------------------------------------------------------------------------------
 // skinny GEMM v2: the weight slab is streamed by TMA into an 8-deep ring of 128B-swizzled tiles
@@ -167,33 +31,37 @@ skinny_gemm_kernel(const bf16* __restrict__ x, long long ldx, const bf16* __rest
 // registers on them; one producer lane + four consumer warps (2 k32-chunks each per stage, same
 // weight-slab-as-A-operand mma.sync trick as v1). Small-N projections (o_proj, down_proj) no longer pay
 // the load-wait-compute round trips of the register-staged kernel.
-constexpr int SK2_STAGES = 8;
+constexpr int SK2_STAGES = 8;      // default ring depth (16-row slabs: 8 x 8 KB per CTA)
 constexpr int SK2_KT = 256;      // k elements per stage
 constexpr int SK2_THREADS = 160; // warp 0 = TMA producer, warps 1..4 = consumers
 
-template <int ROWS>
+template <int ROWS, int NST = SK2_STAGES>
 __global__ void __launch_bounds__(SK2_THREADS)
-skinny_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const bf16* __restrict__ x, long long ldx,
+skinny_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
                        void* __restrict__ y, long long ldy, const bf16* __restrict__ bias,
                        const bf16* __restrict__ resid, long long ldr, int m, int N, int K, int epi, int out_f32,
-                       int pdl, const void* __restrict__ pf, long long pf_bytes) {
+                       int pdl) {
   constexpr int G = ROWS >= 16 ? ROWS / 16 : 1;
   constexpr bool HALF = ROWS == 8;             // 8-row slab: rows 8..15 of the MMA operand are zero
-  constexpr int BOX = ROWS * 128;              // bytes of one [ROWS x 64 k] TMA box
-  constexpr int STAGE = 4 * BOX;               // 4 boxes = 256 k
+  constexpr int BOX = ROWS * 128;              // bytes of one [ROWS x 64 k] weight box
+  constexpr int XBOX = 8 * 128;                // bytes of one [8 batch rows x 64 k] activation box
+  constexpr int STAGE_W = 4 * BOX;             // 4 boxes = 256 k of the weight slab
+  constexpr int STAGE = STAGE_W + 4 * XBOX;    // + the same 256 k of the activations (rows >= m zero-filled by TMA)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t bar = base + SK2_STAGES * STAGE;
-  float* red = reinterpret_cast<float*>(base_ptr + SK2_STAGES * STAGE + 128);   // [4][ROWS][8]
+  constexpr int BARB = (2 * NST * 8 + 127) & ~127;      // bytes of the full/empty barrier block
+  const uint32_t bar = base + NST * STAGE;
+  float* red = reinterpret_cast<float*>(base_ptr + NST * STAGE + BARB);   // [4][ROWS][8]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * ROWS;
   const int n_kt = (K + SK2_KT - 1) / SK2_KT;
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmap_w);
-    for (int s = 0; s < SK2_STAGES; ++s) {
-      mbar_init(bar + 8 * s, 1);                     // full
-      mbar_init(bar + 8 * (SK2_STAGES + s), 4);      // empty: one arrive per consumer warp
+    prefetch_tmap(&tmap_x);
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(bar + 8 * s, 1);              // full
+      mbar_init(bar + 8 * (NST + s), 4);      // empty: one arrive per consumer warp
     }
     fence_barrier_init();
   }
@@ -201,17 +69,36 @@ skinny_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const bf16* _
   __syncthreads();
   if (warp == 0) {
     if (lane == 0) {
-      // the producer does not wait for the previous kernel: the ring fills with weights while x is being produced
-      for (int kt = 0; kt < n_kt; ++kt) {
-        const int s = kt % SK2_STAGES;
-        const uint32_t ph = (uint32_t)((kt / SK2_STAGES) & 1);
-        mbar_wait(bar + 8 * (SK2_STAGES + s), ph ^ 1);
+      // The activation slice of a stage travels WITH its weights: one transaction, NST stages of look-ahead. (Round 1
+      // fetched each lane's x fragments through a private 2-deep cp.async ring: every stage then waited an L2 round trip
+      // for fragments requested two stages earlier, which capped a CTA at ~30 GB/s whatever the ring depth —
+      // profiles/r02_decode_skinny_gemm.txt.) The weights of the first NST stages are requested BEFORE waiting for the
+      // previous kernel (they never change during a step); x, which that kernel produces, follows after the wait.
+      const int n_pre = n_kt < NST ? n_kt : NST;
+      for (int kt = 0; kt < n_pre; ++kt) {
+        mbar_arrive_expect_tx(bar + 8 * kt, STAGE);
+#pragma unroll
+        for (int bx = 0; bx < 4; ++bx)
+          tma_load_2d(base + kt * STAGE + bx * BOX, &tmap_w, bar + 8 * kt, kt * SK2_KT + bx * 64, n0);
+      }
+      griddep_wait();
+      for (int kt = 0; kt < n_pre; ++kt) {
+#pragma unroll
+        for (int bx = 0; bx < 4; ++bx)
+          tma_load_2d(base + kt * STAGE + STAGE_W + bx * XBOX, &tmap_x, bar + 8 * kt, kt * SK2_KT + bx * 64, 0);
+      }
+      for (int kt = n_pre; kt < n_kt; ++kt) {
+        const int s = kt % NST;
+        const uint32_t ph = (uint32_t)((kt / NST) & 1);
+        mbar_wait(bar + 8 * (NST + s), ph ^ 1);
         mbar_arrive_expect_tx(bar + 8 * s, STAGE);
 #pragma unroll
         for (int bx = 0; bx < 4; ++bx)
           tma_load_2d(base + s * STAGE + bx * BOX, &tmap_w, bar + 8 * s, kt * SK2_KT + bx * 64, n0);
+#pragma unroll
+        for (int bx = 0; bx < 4; ++bx)
+          tma_load_2d(base + s * STAGE + STAGE_W + bx * XBOX, &tmap_x, bar + 8 * s, kt * SK2_KT + bx * 64, 0);
       }
-      l2_prefetch_share(pf, pf_bytes);       // this CTA's weight stream is fully requested: start on the next kernel's
     }
   } else {
     const int cw = warp - 1;                 // consumer index 0..3
@@ -221,32 +108,9 @@ skinny_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const bf16* _
     for (int i = 0; i < G; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    const bf16* xrow = x + (long long)g * ldx;
-    const bool xok = g < m;
-    griddep_wait();                          // x (and later y/resid) belong to the previous kernel
-    // The x fragments come from L2: every lane streams exactly the fragments it feeds to its own MMAs through a
-    // private SK2_XP-deep cp.async ring in shared memory (register prefetching does not get deeper than ~1 stage:
-    // in-flight loads share a handful of scoreboards, so waiting for the oldest waits for the newest as well).
-    constexpr int SK2_XP = 2;
-    const uint32_t xring = base + SK2_STAGES * STAGE + 128 + 4 * ROWS * 8 * 4 + (threadIdx.x - 32) * 16;
-    uint8_t* xring_ptr = base_ptr + SK2_STAGES * STAGE + 128 + 4 * ROWS * 8 * 4 + (threadIdx.x - 32) * 16;
-    auto fetch_x = [&](int kt) {
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int k0 = kt * SK2_KT + (2 * cw + u) * 32 + t * 8;
-        const bool ok = xok && k0 < K;
-        cp_async16(xring + (kt % SK2_XP) * 4096 + u * 2048, ok ? (const void*)(xrow + k0) : (const void*)x, ok);
-      }
-      cp_async_commit();
-    };
-#pragma unroll
-    for (int j = 0; j < SK2_XP; ++j) fetch_x(j);
     for (int kt = 0; kt < n_kt; ++kt) {
-      const int s = kt % SK2_STAGES;
-      const uint32_t ph = (uint32_t)((kt / SK2_STAGES) & 1);
-      cp_async_wait<SK2_XP - 1>();
-      const uint8_t* xsrc = xring_ptr + (kt % SK2_XP) * 4096;
-      const int4 xb[2] = {*reinterpret_cast<const int4*>(xsrc), *reinterpret_cast<const int4*>(xsrc + 2048)};
+      const int s = kt % NST;
+      const uint32_t ph = (uint32_t)((kt / NST) & 1);
       mbar_wait(bar + 8 * s, ph);
       const uint8_t* st = base_ptr + s * STAGE;
 #pragma unroll
@@ -254,6 +118,8 @@ skinny_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const bf16* _
         const int cc = 2 * cw + u;             // k32 chunk of this stage: box cc/2, half cc%2
         const uint8_t* bx = st + (cc >> 1) * BOX;
         const int chunk = (cc & 1) * 4 + t;    // 16-byte chunk index inside the 128-byte row
+        // B fragment: batch row g, the same 8 k values (128-byte swizzled [8 x 64] box)
+        const int4 xb = *reinterpret_cast<const int4*>(st + STAGE_W + (cc >> 1) * XBOX + g * 128 + ((chunk ^ g) << 4));
 #pragma unroll
         for (int i = 0; i < G; ++i) {
           const int r0 = i * 16 + g, r1 = r0 + 8;
@@ -262,15 +128,13 @@ skinny_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const bf16* _
                                : *reinterpret_cast<const int4*>(bx + r1 * 128 + ((chunk ^ (r1 & 7)) << 4));
           const uint32_t a1[4] = {(uint32_t)w0.x, (uint32_t)w1.x, (uint32_t)w0.y, (uint32_t)w1.y};
           const uint32_t a2[4] = {(uint32_t)w0.z, (uint32_t)w1.z, (uint32_t)w0.w, (uint32_t)w1.w};
-          mma_bf16_16816(acc[i], a1, (uint32_t)xb[u].x, (uint32_t)xb[u].y);
-          mma_bf16_16816(acc[i], a2, (uint32_t)xb[u].z, (uint32_t)xb[u].w);
+          mma_bf16_16816(acc[i], a1, (uint32_t)xb.x, (uint32_t)xb.y);
+          mma_bf16_16816(acc[i], a2, (uint32_t)xb.z, (uint32_t)xb.w);
         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar + 8 * (SK2_STAGES + s));
-      fetch_x(kt + SK2_XP);
+      if (lane == 0) mbar_arrive(bar + 8 * (NST + s));
     }
-    cp_async_wait<0>();
 #pragma unroll
     for (int i = 0; i < G; ++i) {
       red[(cw * ROWS + i * 16 + g) * 8 + 2 * t] = acc[i][0];
@@ -328,8 +192,7 @@ __global__ void __launch_bounds__(DA_THREADS)
 decode_attn_kernel(const bf16* __restrict__ qkv, long long ldqkv, bf16* __restrict__ kc,
                    bf16* __restrict__ vc, const int* __restrict__ pos_arr,
                    const float* __restrict__ cos_t, const float* __restrict__ sin_t,
-                   float* __restrict__ part, int Hq, int Hkv, int Tmax, int S, float scale,
-                   const void* __restrict__ pf, long long pf_bytes) {
+                   float* __restrict__ part, int Hq, int Hkv, int Tmax, int S, float scale) {
   extern __shared__ float sm[];
   float* sq = sm;                          // [G][128] rotated, scaled q
   float* sknew = sq + G * DA_D;            // [128] rotated new k
@@ -338,7 +201,6 @@ decode_attn_kernel(const bf16* __restrict__ qkv, long long ldqkv, bf16* __restri
   float* sscore = sred + 8 * G * DA_D;     // [G][chunk_pad]
   const int hk = blockIdx.x, b = blockIdx.y, sp = blockIdx.z;
   griddep_launch();
-  if (threadIdx.x == 0) l2_prefetch_share(pf, pf_bytes);   // attention barely touches HBM: stream the MLP weights meanwhile
   griddep_wait();
   const int pos = pos_arr[b];
   const int n_ctx = pos + 1;
@@ -627,112 +489,95 @@ __global__ void decode_select_hidden_kernel(const int* __restrict__ mode, const 
 
 }  // namespace
 
-MM_API int mm_skinny_gemm_pf(const void* x, const void* W, void* y, const void* bias, const void* resid,
-                             long long ldx, long long ldw, long long ldy, long long ldr, int m, int N,
-                             int K, int epilogue, int out_f32, const void* prefetch, long long prefetch_bytes,
-                             cudaStream_t stream) {
-  MM_CHECK_ARG(m >= 1 && m <= 8, "mm_skinny_gemm: batch must be in [1,8] (m=%d)", m);
-  MM_CHECK_ARG(K % 32 == 0 && ldx % 8 == 0 && ldw % 8 == 0, "mm_skinny_gemm: need K%%32==0, ldx/ldw%%8==0");
-  MM_CHECK_ARG(epilogue >= SK_STORE && epilogue <= SK_SWIGLU, "mm_skinny_gemm: bad epilogue");
-  MM_CHECK_ARG((epilogue != SK_BIAS && epilogue != SK_BIAS_GELU) || bias, "mm_skinny_gemm: bias missing");
-  MM_CHECK_ARG(epilogue != SK_RESID || resid, "mm_skinny_gemm: residual missing");
-  const int pm = mm_pdl_mode();
-  const bool rows32 = (epilogue == SK_SWIGLU) || (N >= 32 * 4 * mm_num_sms());
-  if (epilogue == SK_SWIGLU) MM_CHECK_ARG(N % 32 == 0 && !out_f32, "mm_skinny_gemm: SWIGLU needs N%%32==0");
-  static const bool use_v1 = getenv("MM_SKINNY_V1") != nullptr;
-  // measured on B200 (graph replay, profiles/r01_decode_skinny_gemm.txt): the TMA-pipelined kernel wins on the
-  // 16-row shapes (qkv 12.3 vs 14.8 us, o_proj 9.8 vs 13.8, down_proj 38.4 vs 42.8), the register-staged kernel
-  // on the 32-row ones (gate/up 55.1 vs 57.7, lm_head 182 vs 197)
-  // MM_SKINNY_GU_V2 moves the gate/up projection to the TMA kernel as well (measured slower, also under PDL)
-  static const bool gu_v2 = getenv("MM_SKINNY_GU_V2") != nullptr;
-  const bool v2_ok = !rows32 || (epilogue == SK_SWIGLU && gu_v2);
-  if (!use_v1 && v2_ok && ((uintptr_t)W & 15) == 0) {
-    // TMA-pipelined kernel
-    static PFN_encodeTiledSk enc = nullptr;
-    static std::once_flag once;
-    std::call_once(once, [] {
-      void* fn = nullptr;
-      cudaDriverEntryPointQueryResult q;
-      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
-          q == cudaDriverEntryPointSuccess)
-        enc = reinterpret_cast<PFN_encodeTiledSk>(fn);
-    });
-    MM_CHECK_ARG(enc != nullptr, "mm_skinny_gemm: cuTensorMapEncodeTiled unavailable");
-    static const int rows_override = getenv("MM_SKINNY_ROWS") ? atoi(getenv("MM_SKINNY_ROWS")) : 0;
-    int rows = rows32 ? 32 : 16;
-    // (an 8-row slab variant exists for experiments, MM_SKINNY_ROWS=8; measured slower: 13.4 vs 12.4 us on qkv)
-    if (rows_override == 8 || rows_override == 16) rows = rows_override;
-    CUtensorMap tm;
-    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
-    cuuint64_t strides[1] = {(cuuint64_t)ldw * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(W), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    MM_CHECK_ARG(r == CUDA_SUCCESS, "mm_skinny_gemm: cuTensorMapEncodeTiled failed (%d)", (int)r);
-    const int smem = SK2_STAGES * 4 * rows * 128 + 128 + 4 * rows * 8 * 4 + 2 * 4096 + 1024;
-    if (rows32) {
-      static std::once_flag o32;
-      static cudaError_t e32 = cudaSuccess;
-      std::call_once(o32, [&] {
-        e32 = cudaFuncSetAttribute(skinny_gemm_tma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      });
-      MM_CHECK_CUDA(e32);
-      MM_CHECK_CUDA(launch_pdl(pm & 1, skinny_gemm_tma_kernel<32>, dim3((N + 31) / 32), dim3(SK2_THREADS), smem, stream, tm,
-                               (const bf16*)x, ldx, y, ldy, (const bf16*)bias, (const bf16*)resid, ldr, m, N, K,
-                               epilogue, out_f32, pm, prefetch, prefetch_bytes));
-    } else if (rows == 8) {
-      static std::once_flag o8;
-      static cudaError_t e8 = cudaSuccess;
-      std::call_once(o8, [&] {
-        e8 = cudaFuncSetAttribute(skinny_gemm_tma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      });
-      MM_CHECK_CUDA(e8);
-      MM_CHECK_CUDA(launch_pdl(pm & 1, skinny_gemm_tma_kernel<8>, dim3((N + 7) / 8), dim3(SK2_THREADS), smem, stream, tm,
-                               (const bf16*)x, ldx, y, ldy, (const bf16*)bias, (const bf16*)resid, ldr, m, N, K,
-                               epilogue, out_f32, pm, prefetch, prefetch_bytes));
-    } else {
-      static std::once_flag o16;
-      static cudaError_t e16 = cudaSuccess;
-      std::call_once(o16, [&] {
-        e16 = cudaFuncSetAttribute(skinny_gemm_tma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      });
-      MM_CHECK_CUDA(e16);
-      MM_CHECK_CUDA(launch_pdl(pm & 1, skinny_gemm_tma_kernel<16>, dim3((N + 15) / 16), dim3(SK2_THREADS), smem, stream, tm,
-                               (const bf16*)x, ldx, y, ldy, (const bf16*)bias, (const bf16*)resid, ldr, m, N, K,
-                               epilogue, out_f32, pm, prefetch, prefetch_bytes));
-    }
-    MM_CHECK_LAUNCH();
-    return MM_OK;
-  }
-  if (rows32)
-    MM_CHECK_CUDA(launch_pdl(pm & 1, skinny_gemm_kernel<32>, dim3((N + 31) / 32), dim3(SK_THREADS), 0, stream, (const bf16*)x,
-                             ldx, (const bf16*)W, ldw, y, ldy, (const bf16*)bias, (const bf16*)resid, ldr, m, N, K,
-                             epilogue, out_f32, pm, prefetch, prefetch_bytes));
-  else
-    MM_CHECK_CUDA(launch_pdl(pm & 1, skinny_gemm_kernel<16>, dim3((N + 15) / 16), dim3(SK_THREADS), 0, stream, (const bf16*)x,
-                             ldx, (const bf16*)W, ldw, y, ldy, (const bf16*)bias, (const bf16*)resid, ldr, m, N, K,
-                             epilogue, out_f32, pm, prefetch, prefetch_bytes));
+namespace {
+
+template <int ROWS, int NST>
+int launch_skinny_tma(const CUtensorMap& tw, const CUtensorMap& tx, void* y, long long ldy, const void* bias,
+                      const void* resid, long long ldr, int m, int N, int K, int epilogue, int out_f32, int pm,
+                      cudaStream_t stream) {
+  constexpr int smem = NST * (4 * ROWS * 128 + 4 * 8 * 128) + ((2 * NST * 8 + 127) & ~127) + 4 * ROWS * 8 * 4 + 1024;
+  static std::once_flag once;
+  static cudaError_t err = cudaSuccess;
+  std::call_once(once, [&] {
+    err = cudaFuncSetAttribute(skinny_gemm_tma_kernel<ROWS, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  });
+  MM_CHECK_CUDA(err);
+  MM_CHECK_CUDA(launch_pdl(pm & 1, skinny_gemm_tma_kernel<ROWS, NST>, dim3((N + ROWS - 1) / ROWS), dim3(SK2_THREADS), smem,
+                           stream, tw, tx, y, ldy, (const bf16*)bias, (const bf16*)resid, ldr, m, N, K, epilogue, out_f32,
+                           pm));
   MM_CHECK_LAUNCH();
   return MM_OK;
 }
 
+}  // namespace
+
 MM_API int mm_skinny_gemm(const void* x, const void* W, void* y, const void* bias, const void* resid,
                           long long ldx, long long ldw, long long ldy, long long ldr, int m, int N,
                           int K, int epilogue, int out_f32, cudaStream_t stream) {
-  return mm_skinny_gemm_pf(x, W, y, bias, resid, ldx, ldw, ldy, ldr, m, N, K, epilogue, out_f32, nullptr, 0, stream);
+  MM_CHECK_ARG(m >= 1 && m <= 8, "mm_skinny_gemm: batch must be in [1,8] (m=%d)", m);
+  MM_CHECK_ARG(K % 32 == 0 && ldx % 8 == 0 && ldw % 8 == 0, "mm_skinny_gemm: need K%%32==0, ldx/ldw%%8==0");
+  MM_CHECK_ARG(((uintptr_t)W & 15) == 0 && ((uintptr_t)x & 15) == 0, "mm_skinny_gemm: x / W must be 16-byte aligned");
+  MM_CHECK_ARG(epilogue >= SK_STORE && epilogue <= SK_SWIGLU, "mm_skinny_gemm: bad epilogue");
+  MM_CHECK_ARG((epilogue != SK_BIAS && epilogue != SK_BIAS_GELU) || bias, "mm_skinny_gemm: bias missing");
+  MM_CHECK_ARG(epilogue != SK_RESID || resid, "mm_skinny_gemm: residual missing");
+  const int pm = mm_pdl_mode();
+  // 32-row slabs where the epilogue needs them (SwiGLU: 16 gate + 16 up rows of the same channels) and for very
+  // large N (lm_head: fewer, longer-lived CTAs); 16-row slabs otherwise
+  const bool rows32 = (epilogue == SK_SWIGLU) || (N >= 32 * 4 * mm_num_sms());
+  if (epilogue == SK_SWIGLU) MM_CHECK_ARG(N % 32 == 0 && !out_f32, "mm_skinny_gemm: SWIGLU needs N%%32==0");
+  static PFN_encodeTiledSk enc = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      enc = reinterpret_cast<PFN_encodeTiledSk>(fn);
+  });
+  MM_CHECK_ARG(enc != nullptr, "mm_skinny_gemm: cuTensorMapEncodeTiled unavailable");
+  CUtensorMap tw, tx;
+  cuuint32_t estr[2] = {1, 1};
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
+    cuuint64_t strides[1] = {(cuuint64_t)ldw * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)(rows32 ? 32 : 16)};
+    CUresult r = enc(&tw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(W), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MM_CHECK_ARG(r == CUDA_SUCCESS, "mm_skinny_gemm: cuTensorMapEncodeTiled(W) failed (%d)", (int)r);
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)m};            // rows >= m of the 8-row box are zero-filled
+    cuuint64_t strides[1] = {(cuuint64_t)ldx * 2};
+    cuuint32_t box[2] = {64, 8};
+    CUresult r = enc(&tx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(x), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MM_CHECK_ARG(r == CUDA_SUCCESS, "mm_skinny_gemm: cuTensorMapEncodeTiled(x) failed (%d)", (int)r);
+  }
+  // ring depth (MM_SK2_STAGES / MM_SK2_STAGES32, read once): experiments only
+  static const int nst16 = getenv("MM_SK2_STAGES") ? atoi(getenv("MM_SK2_STAGES")) : 0;
+  static const int nst32 = getenv("MM_SK2_STAGES32") ? atoi(getenv("MM_SK2_STAGES32")) : 0;
+#define MM_SK(R, S) return launch_skinny_tma<R, S>(tw, tx, y, ldy, bias, resid, ldr, m, N, K, epilogue, out_f32, pm, stream)
+  if (rows32) {
+    if (nst32 == 4) MM_SK(32, 4);
+    if (nst32 == 10) MM_SK(32, 10);
+    MM_SK(32, 5);
+  }
+  if (nst16 == 5) MM_SK(16, 5);
+  if (nst16 == 6) MM_SK(16, 6);
+  MM_SK(16, 8);
+#undef MM_SK
 }
 
 MM_API long long mm_decode_attn_workspace_bytes(int B, int Hq, int Hkv, int splits) {
   return (long long)B * Hkv * splits * (Hq / Hkv) * (2 + DA_D) * 4;
 }
 
-MM_API int mm_decode_attn_pf(const void* qkv, long long ldqkv, void* kcache, void* vcache, const int* pos,
-                             const float* cos_t, const float* sin_t, void* out, long long ldo, int B,
-                             int Hq, int Hkv, int head_dim, int Tmax, float scale, void* workspace,
-                             long long workspace_bytes, int splits, const void* prefetch, long long prefetch_bytes,
-                             cudaStream_t stream) {
+MM_API int mm_decode_attn(const void* qkv, long long ldqkv, void* kcache, void* vcache, const int* pos,
+                          const float* cos_t, const float* sin_t, void* out, long long ldo, int B,
+                          int Hq, int Hkv, int head_dim, int Tmax, float scale, void* workspace,
+                          long long workspace_bytes, int splits, cudaStream_t stream) {
   MM_CHECK_ARG(head_dim == DA_D && Hq % Hkv == 0, "mm_decode_attn: need head_dim 128");
   const int G = Hq / Hkv;
   MM_CHECK_ARG(G == 1 || G == 2 || G == 4 || G == 8, "mm_decode_attn: GQA group must be 1, 2, 4 or 8");
@@ -750,7 +595,7 @@ MM_API int mm_decode_attn_pf(const void* qkv, long long ldqkv, void* kcache, voi
                                          (int)smem));                                                        \
     MM_CHECK_CUDA(launch_pdl(mm_pdl_mode() & 2, decode_attn_kernel<GG>, grid, dim3(DA_THREADS), smem, stream, (const bf16*)qkv,  \
                              ldqkv, (bf16*)kcache, (bf16*)vcache, pos, cos_t, sin_t, (float*)workspace, Hq,   \
-                             Hkv, Tmax, splits, scale, prefetch, prefetch_bytes));                           \
+                             Hkv, Tmax, splits, scale));                                                     \
   } while (0)
   if (G == 1) MM_DA_LAUNCH(1);
   else if (G == 2) MM_DA_LAUNCH(2);
@@ -762,14 +607,6 @@ MM_API int mm_decode_attn_pf(const void* qkv, long long ldqkv, void* kcache, voi
                            (bf16*)out, ldo, Hkv, G, splits));
   MM_CHECK_LAUNCH();
   return MM_OK;
-}
-
-MM_API int mm_decode_attn(const void* qkv, long long ldqkv, void* kcache, void* vcache, const int* pos,
-                          const float* cos_t, const float* sin_t, void* out, long long ldo, int B,
-                          int Hq, int Hkv, int head_dim, int Tmax, float scale, void* workspace,
-                          long long workspace_bytes, int splits, cudaStream_t stream) {
-  return mm_decode_attn_pf(qkv, ldqkv, kcache, vcache, pos, cos_t, sin_t, out, ldo, B, Hq, Hkv, head_dim, Tmax, scale,
-                           workspace, workspace_bytes, splits, nullptr, 0, stream);
 }
 
 MM_API int mm_kv_prefill(const void* qkv, long long ld, void* kcache, void* vcache, int B, int T, int Hq,

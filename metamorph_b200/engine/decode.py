@@ -14,7 +14,7 @@ import torch
 
 from .. import ops
 from ..constants import EOS_TOKEN_IDS, IMAGE_END_TOKEN_ID, IMAGE_START_TOKEN_ID
-from .decode_step import decode_heads, decoder_stack_step, heads_first_weight
+from .decode_step import decode_heads, decoder_stack_step
 from .llama import StackContext
 
 
@@ -85,8 +85,7 @@ class DecodeEngine:
         logits = torch.empty((B, (V + 7) // 8 * 8), dtype=torch.float32, device=dev)
 
         def heads_and_state(h_pre_norm, step):
-            tok, pred_z, prediction = decode_heads(m, h_pre_norm, st["in_image_mode"], logits, V,
-                                                   next_step_first=layers[0].wqkv)
+            tok, pred_z, prediction = decode_heads(m, h_pre_norm, st["in_image_mode"], logits, V)
             ops.decode_state_step(st, tok, forced, step, B, ntok, max_new_tokens, start_image_token_id,
                                   end_image_token_id, eos0, eos1, pred_z, img_out)
             ops.decode_next_input(st["append_kind"], st["next_token"], model.embed_tokens.weight.data,
@@ -98,7 +97,7 @@ class DecodeEngine:
 
         def one_step_body():
             # position of the token being fed = pos - 1 (the state step already advanced pos)
-            return decoder_stack_step(layers, xin, kc, vc, st["pos"] - 1, stack, after=heads_first_weight(m))
+            return decoder_stack_step(layers, xin, kc, vc, st["pos"] - 1, stack)
 
         # One captured CUDA graph is replayed for every step (launch-bound inner loop): all per-step state,
         # including the index into the forced-token schedule, lives in device memory.

@@ -23,7 +23,7 @@ import torch
 
 from .. import ops
 from ..constants import EOS_TOKEN_IDS, IMAGE_END_TOKEN_ID, IMAGE_START_TOKEN_ID
-from .decode_step import decode_heads, decoder_stack_step, heads_first_weight
+from .decode_step import decode_heads, decoder_stack_step
 from .llama import StackContext
 
 
@@ -93,10 +93,8 @@ class ContinuousBatcher:
     # ------------------------------------------------------------------ one device step for all slots
     def _step_body(self):
         st = self.st
-        x = decoder_stack_step(self.layers, self.xin, self.kc, self.vc, st["pos"] - 1, self.stack,
-                               after=heads_first_weight(self.m))
-        tok, pred_z, prediction = decode_heads(self.m, x, st["in_image_mode"], self.logits, self.V,
-                                                   next_step_first=self.layers[0].wqkv)
+        x = decoder_stack_step(self.layers, self.xin, self.kc, self.vc, st["pos"] - 1, self.stack)
+        tok, pred_z, prediction = decode_heads(self.m, x, st["in_image_mode"], self.logits, self.V)
         ops.decode_state_step_slots(st, tok, self.forced, self.max_new_slot, self.B, self.ntok, self.start_id,
                                     self.end_id, self.eos0, self.eos1, pred_z, self.img_out)
         ops.decode_next_input(st["append_kind"], st["next_token"], self.inner.embed_tokens.weight.data, prediction,

@@ -395,40 +395,21 @@ ctypes_ll = _ctypes.c_longlong
 SK_STORE, SK_BIAS, SK_RESID, SK_BIAS_GELU, SK_SWIGLU = range(5)
 
 
-def _pf(prefetch):
-    """prefetch = a tensor (its first 48 MB), or (tensor, byte offset, byte count) -> (pointer, bytes)."""
-    if prefetch is None:
-        return c_void_p(0), ll(0)
-    if isinstance(prefetch, tuple):
-        t, off, n = prefetch
-    else:
-        t, off, n = prefetch, 0, PREFETCH_CAP
-    total = t.numel() * t.element_size()
-    off = min(off, total) & ~127
-    n = max(0, min(n, total - off))
-    return c_void_p(t.data_ptr() + off), ll(n)
-
-
-PREFETCH_CAP = 48 << 20     # bytes of the next kernel's weights requested ahead: well inside the 126 MB L2
-
-
-def skinny_gemm(x, w, *, bias=None, resid=None, epilogue=SK_STORE, out=None, out_dtype=torch.bfloat16, prefetch=None):
-    """y[m<=8, N] = x[m, K] w[N, K]^T — HBM-bound weight streaming for the decode step. `prefetch`: the weight matrix
-    the NEXT kernel of the step will stream (L2 hint, see include/metamorph_b200.h)."""
+def skinny_gemm(x, w, *, bias=None, resid=None, epilogue=SK_STORE, out=None, out_dtype=torch.bfloat16):
+    """y[m<=8, N] = x[m, K] w[N, K]^T — HBM-bound weight streaming for the decode step."""
     require_cuda(x, w, bias, resid, out)
     m, K = x.shape
     N = w.shape[0]
     n_out = N // 2 if epilogue == SK_SWIGLU else N
     if out is None:
         out = torch.empty((m, n_out), dtype=out_dtype, device=x.device)
-    pf_ptr, pf_n = _pf(prefetch)
-    call("mm_skinny_gemm_pf", ptr(x), ptr(w), ptr(out), ptr(bias), ptr(resid), ll(x.stride(0)),
+    call("mm_skinny_gemm", ptr(x), ptr(w), ptr(out), ptr(bias), ptr(resid), ll(x.stride(0)),
          ll(w.stride(0)), ll(out.stride(0)), ll(resid.stride(0) if resid is not None else 0), c_int(m),
-         c_int(N), c_int(K), c_int(epilogue), c_int(1 if out.dtype == torch.float32 else 0), pf_ptr, pf_n, stream_ptr())
+         c_int(N), c_int(K), c_int(epilogue), c_int(1 if out.dtype == torch.float32 else 0), stream_ptr())
     return out
 
 
-def decode_attn(qkv, kcache, vcache, pos, cos, sin, Hq, Hkv, head_dim, scale, out=None, splits=None, prefetch=None):
+def decode_attn(qkv, kcache, vcache, pos, cos, sin, Hq, Hkv, head_dim, scale, out=None, splits=None):
     require_cuda(qkv, kcache, vcache, pos, cos, sin)
     B = qkv.shape[0]
     Tmax = kcache.shape[2]
@@ -437,10 +418,9 @@ def decode_attn(qkv, kcache, vcache, pos, cos, sin, Hq, Hkv, head_dim, scale, ou
     if out is None:
         out = torch.empty((B, Hq * head_dim), dtype=torch.bfloat16, device=qkv.device)
     ws = _workspace("decode_attn", B * Hkv * splits * (Hq // Hkv) * (2 + head_dim) * 4, qkv.device)
-    pf_ptr, pf_n = _pf(prefetch)
-    call("mm_decode_attn_pf", ptr(qkv), ll(qkv.stride(0)), ptr(kcache), ptr(vcache), ptr(pos), ptr(cos),
+    call("mm_decode_attn", ptr(qkv), ll(qkv.stride(0)), ptr(kcache), ptr(vcache), ptr(pos), ptr(cos),
          ptr(sin), ptr(out), ll(out.stride(0)), c_int(B), c_int(Hq), c_int(Hkv), c_int(head_dim),
-         c_int(Tmax), c_float(scale), ptr(ws), ll(ws.numel()), c_int(splits), pf_ptr, pf_n, stream_ptr())
+         c_int(Tmax), c_float(scale), ptr(ws), ll(ws.numel()), c_int(splits), stream_ptr())
     return out
 
 

@@ -39,5 +39,3 @@ bench(4096, 14336, ops.SK_RESID)
 bench(128258, 4096, copies=3)
 
 import os
-if os.environ.get("MM_SKINNY_V1") is None:
-    print("(v2 TMA kernel; set MM_SKINNY_V1=1 for the register-staged kernel)")
