@@ -27,7 +27,7 @@ int mm_pdl_mode() {
   static const int mode = [] {
     if (!mm_pdl_enabled()) return 0;
     const char* e = getenv("MM_PDL_MODE");
-    return e ? atoi(e) : 9;
+    return e ? atoi(e) : 3;
   }();
   return mode;
 }

@@ -49,11 +49,11 @@ static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b;
 int mm_num_sms();
 // programmatic dependent launch (PDL) for the decode chain: 1 unless MM_PDL=0 (api.cu)
 int mm_pdl_enabled();
-// experiment switches (MM_PDL_MODE bitmask, default 9 = GEMMs only, late trigger; B200 sweep of the 512-step decode:
-// off 4.586 ms/step, 1: 4.675, 3: 4.883, 9: 4.617 (4.495 with gate/up on the register-staged kernel), 11: 4.567 —
-// an early trigger lets the next GEMM's CTAs pile onto the first idle SMs and unbalances its weight stream): 1 = weight-streaming GEMMs launched with the PDL attribute,
-// 2 = the small decode kernels too, 4 = L2 prefetch in the register-staged GEMM prologue, 8 = trigger dependents
-// after the main loop instead of at kernel entry
+// MM_PDL_MODE bitmask (default 3): 1 = weight-streaming GEMMs launched with the PDL attribute, 2 = the small decode kernels
+// too, 8 = trigger dependents after the main loop instead of at kernel entry. B200 sweep of the 512-step batch-8 decode with
+// the round-2 TMA kernel (activations travel with the weight stage): off 3.836 ms/step, 1: 3.617, 3: 3.609, 9: 3.694,
+// 11: 3.678 — the early trigger lets the next kernel's producer fill its ring with weights while this one drains
+// (round 1's register-staged kernels preferred the late trigger, mode 9).
 int mm_pdl_mode();
 
 // ----------------------------------------------------------------------------------------------

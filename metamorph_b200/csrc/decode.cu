@@ -523,7 +523,8 @@ MM_API int mm_skinny_gemm(const void* x, const void* W, void* y, const void* bia
   const int pm = mm_pdl_mode();
   // 32-row slabs where the epilogue needs them (SwiGLU: 16 gate + 16 up rows of the same channels) and for very
   // large N (lm_head: fewer, longer-lived CTAs); 16-row slabs otherwise
-  const bool rows32 = (epilogue == SK_SWIGLU) || (N >= 32 * 4 * mm_num_sms());
+  static const int rows_env = getenv("MM_SK2_ROWS") ? atoi(getenv("MM_SK2_ROWS")) : 0;   // experiments: 32 = 32-row slabs everywhere
+  const bool rows32 = (epilogue == SK_SWIGLU) || (N >= 32 * 4 * mm_num_sms()) || (rows_env == 32 && N % 32 == 0);
   if (epilogue == SK_SWIGLU) MM_CHECK_ARG(N % 32 == 0 && !out_f32, "mm_skinny_gemm: SWIGLU needs N%%32==0");
   static PFN_encodeTiledSk enc = nullptr;
   static std::once_flag once;
