@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
     ap.add_argument("--no-shard", action="store_true", help="A/B only: replicate the optimizer state (round-1 behaviour)")
+    ap.add_argument("--no-fused-allgather", action="store_true", help="A/B only: NCCL all-gather instead of the AdamW kernel's own broadcast")
     ap.add_argument("--extra-configs", default="auto", choices=["auto", "on", "off"],
                     help="BASELINE configs 3 (batch 8/GPU) and 5 (T=8192, 8 frames) as extra keys; auto = at 8 GPUs")
     return ap.parse_args()
@@ -402,7 +403,8 @@ def main():
     cfg = synthetic.make_config(llama=dict(num_hidden_layers=args.layers), max_len=args.seq_len)
     model = synthetic.build_model(cfg, device=dev)
     engine = TrainEngine(model, lr=6.93e-5, weight_decay=0.0, max_grad_norm=None, total_steps=1000,
-                         n_save_gu_layers=min(args.save_gu_layers, args.layers), shard_optimizer=not args.no_shard)
+                         n_save_gu_layers=min(args.save_gu_layers, args.layers), shard_optimizer=not args.no_shard,
+                         fused_allgather=not args.no_fused_allgather)
     B, T = args.batch, args.seq_len
     host_batch = synthetic.train_batch(B, T, n_prompt_images=args.images_per_sample // 2,
                                        n_answer_images=args.images_per_sample - args.images_per_sample // 2,
@@ -501,6 +503,17 @@ def main():
             try:
                 torch.cuda.empty_cache()
                 torch.cuda.reset_peak_memory_stats()
+                # activations of the bigger shape on top of what is resident: run it only if EVERY rank has the room (an
+                # out-of-memory error on one rank in the middle of a step would leave the others inside a collective)
+                tok_x = b_x * t_x
+                need = tok_x * (args.layers * (40960 + 57344 * min(args.save_gu_layers, args.layers) / max(args.layers, 1))
+                                + 4 * 57344 + 3 * 128264) + (6 << 30)
+                free = torch.tensor([torch.cuda.mem_get_info()[0]], dtype=torch.float64, device=dev)
+                if world > 1:
+                    dist.all_reduce(free, op=dist.ReduceOp.MIN)
+                if float(free) < need:
+                    extra[key] = {"skipped": f"needs ~{need / 1e9:.0f} GB free per GPU, {float(free) / 1e9:.0f} GB available"}
+                    continue
                 model.config.tokenizer_model_max_length = t_x
                 hb = synthetic.train_batch(b_x, t_x, n_prompt_images=imgs_x // 2, n_answer_images=imgs_x - imgs_x // 2,
                                            seed=4321 + 1000 * rank)
@@ -550,7 +563,10 @@ def main():
                            "l2_policy": "inputs+weights (>100 GB/step) far exceed the 126 MB L2; no flush needed",
                            "max_grad_norm": None,
                            "optimizer": "AdamW fused into the backward sweep, fp32 master/m/v " +
-                                        (f"sharded over the {world} ranks (ZeRO-1: reduce-scatter -> AdamW on the slice -> all-gather)"
+                                        ((f"sharded over the {world} ranks (ZeRO-1: reduce-scatter -> AdamW on the slice, "
+                                          + ("the same kernel broadcasts the updated slice into every replica (symmetric memory"
+                                             + (", NVSwitch multicast)" if engine.fused_allgather and int(engine.layer_buckets[0].symm.multicast_ptr or 0) and engine.use_multicast else ", P2P stores)")
+                                             if engine.fused_allgather else "-> NCCL all-gather") + ")")
                                          if engine.shard_world > 1 else "on this GPU"),
                            "optimizer_state_gb_per_gpu": round(engine.optimizer_state_bytes() / 1e9, 2),
                            "recompute": f"gate/up GEMM recomputed in {args.layers - min(args.save_gu_layers, args.layers)} of {args.layers} layers; norms always",

@@ -90,6 +90,15 @@ int mm_argmax_rows(const float* logits, long long ld, long long R, int V, int* o
 int mm_adamw_step(void* p16, float* p32, float* m, float* v, const void* grad, int grad_f32, long long n, float lr,
                   float beta1, float beta2, float eps, float wd, int step, const float* grad_scale_ptr,
                   float grad_scale, cudaStream_t s);
+/* Sharded-optimizer step with its all-gather fused in: AdamW on this rank's slice, and the updated bf16 slice is written
+ * into EVERY rank's replica of the parameter buffer by the same kernel — through the NVSwitch multicast address of the
+ * (symmetric) buffer (multimem.st) when multicast_p16 != NULL, else with one store per peer over NVLink P2P (peers = device
+ * array of the n_peers buffer base pointers, slice_offset = first element of the slice). Replaces DeepSpeed ZeRO's
+ * all-gather of updated parameters (scripts/zero2.json `allgather_bucket_size`). */
+int mm_adamw_step_bcast(void* multicast_p16, const void* const* peers, int n_peers, long long slice_offset, float* p32,
+                        float* m, float* v, const void* grad, int grad_f32, long long n, float lr, float beta1,
+                        float beta2, float eps, float wd, int step, const float* grad_scale_ptr, float grad_scale,
+                        cudaStream_t s);
 int mm_clip_coef(const float* sumsq, float* out2, float max_norm, cudaStream_t s);
 
 /* Attention: LLaMA causal GQA (modeling_llama.py:199-220) forward/backward, SigLIP MHA forward

@@ -8,12 +8,16 @@
 
 namespace {
 
-template <bool GRAD_F32>
+// BCAST: the updated bf16 values are not stored locally but BROADCAST to every rank's replica of the parameter buffer in
+// the same kernel (the all-gather of a sharded-optimizer step fused into the optimizer): one multimem.st through the
+// NVSwitch multicast mapping of the symmetric buffer when the fabric offers it (NVLS), else one st.global per peer over
+// NVLink P2P. The compute step (AdamW on this rank's slice) and its collective (all-gather of the slice) are ONE kernel.
+template <bool GRAD_F32, bool BCAST>
 __global__ void adamw_kernel(bf16* __restrict__ p16, float* __restrict__ p32, float* __restrict__ m,
                              float* __restrict__ v, const void* __restrict__ grad, long long n4,
                              float lr, float b1, float b2, float eps, float wd, float c1,
                              float sqrt_c2, const float* __restrict__ grad_scale_ptr,
-                             float grad_scale) {
+                             float grad_scale, bf16* const* __restrict__ peers, int n_peers) {
   float gs = grad_scale;
   if (grad_scale_ptr != nullptr) gs *= *grad_scale_ptr;
   const float step = lr / c1;
@@ -48,7 +52,16 @@ __global__ void adamw_kernel(bf16* __restrict__ p16, float* __restrict__ p32, fl
     uint2 o;
     o.x = pack_bf16x2(pp[0], pp[1]);
     o.y = pack_bf16x2(pp[2], pp[3]);
-    *reinterpret_cast<uint2*>(p16 + i * 4) = o;
+    if (!BCAST) {
+      *reinterpret_cast<uint2*>(p16 + i * 4) = o;
+    } else if (peers == nullptr) {      // p16 = multicast address of this slice: one store, the switch replicates it
+      asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" ::"l"(p16 + i * 4), "f"(__uint_as_float(o.x)),
+                   "f"(__uint_as_float(o.y))
+                   : "memory");
+    } else {                            // p16 = OFFSET of the slice (in elements) inside every peer's buffer
+      const long long off = reinterpret_cast<long long>(p16) / 2;
+      for (int r = 0; r < n_peers; ++r) *reinterpret_cast<uint2*>(peers[r] + off + i * 4) = o;
+    }
   }
 }
 
@@ -76,13 +89,39 @@ MM_API int mm_adamw_step(void* p16, float* p32, float* m, float* v, const void* 
   const long long cap = (long long)mm_num_sms() * 16;
   if (blocks > cap) blocks = cap;
   if (grad_f32)
-    adamw_kernel<true><<<(int)blocks, 256, 0, stream>>>((bf16*)p16, p32, m, v, grad, n4, lr, beta1,
-                                                        beta2, eps, wd, c1, sqrt_c2, grad_scale_ptr,
-                                                        grad_scale);
+    adamw_kernel<true, false><<<(int)blocks, 256, 0, stream>>>((bf16*)p16, p32, m, v, grad, n4, lr, beta1, beta2, eps, wd,
+                                                               c1, sqrt_c2, grad_scale_ptr, grad_scale, nullptr, 0);
   else
-    adamw_kernel<false><<<(int)blocks, 256, 0, stream>>>((bf16*)p16, p32, m, v, grad, n4, lr, beta1,
-                                                         beta2, eps, wd, c1, sqrt_c2, grad_scale_ptr,
-                                                         grad_scale);
+    adamw_kernel<false, false><<<(int)blocks, 256, 0, stream>>>((bf16*)p16, p32, m, v, grad, n4, lr, beta1, beta2, eps, wd,
+                                                                c1, sqrt_c2, grad_scale_ptr, grad_scale, nullptr, 0);
+  MM_CHECK_LAUNCH();
+  return MM_OK;
+}
+
+// AdamW on this rank's slice + broadcast of the updated bf16 slice into every rank's parameter buffer (see adamw_kernel).
+// multicast_p16 != NULL: the multicast (NVLS) address of the slice; else peers = DEVICE array of n_peers buffer base
+// pointers and slice_offset = first element of the slice inside each of them.
+MM_API int mm_adamw_step_bcast(void* multicast_p16, const void* const* peers, int n_peers, long long slice_offset,
+                               float* p32, float* m, float* v, const void* grad, int grad_f32, long long n, float lr,
+                               float beta1, float beta2, float eps, float wd, int step, const float* grad_scale_ptr,
+                               float grad_scale, cudaStream_t stream) {
+  MM_CHECK_ARG(n > 0 && n % 4 == 0 && slice_offset % 4 == 0, "mm_adamw_step_bcast: n / offset must be multiples of 4");
+  MM_CHECK_ARG(step >= 1, "mm_adamw_step_bcast: step starts at 1");
+  MM_CHECK_ARG(multicast_p16 != nullptr || (peers != nullptr && n_peers > 0), "mm_adamw_step_bcast: no destination");
+  const float c1 = 1.f - powf(beta1, (float)step);
+  const float sqrt_c2 = sqrtf(1.f - powf(beta2, (float)step));
+  const long long n4 = n / 4;
+  long long blocks = ceil_div64(n4, 256);
+  const long long cap = (long long)mm_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  bf16* dst = multicast_p16 ? (bf16*)multicast_p16 : reinterpret_cast<bf16*>(slice_offset * 2);   // address or byte offset
+  bf16* const* pr = multicast_p16 ? nullptr : (bf16* const*)peers;
+  if (grad_f32)
+    adamw_kernel<true, true><<<(int)blocks, 256, 0, stream>>>(dst, p32, m, v, grad, n4, lr, beta1, beta2, eps, wd, c1, sqrt_c2,
+                                                              grad_scale_ptr, grad_scale, pr, n_peers);
+  else
+    adamw_kernel<false, true><<<(int)blocks, 256, 0, stream>>>(dst, p32, m, v, grad, n4, lr, beta1, beta2, eps, wd, c1,
+                                                               sqrt_c2, grad_scale_ptr, grad_scale, pr, n_peers);
   MM_CHECK_LAUNCH();
   return MM_OK;
 }

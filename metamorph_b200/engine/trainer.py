@@ -29,6 +29,7 @@ Optimizer = torch.optim.AdamW semantics (reference: --optim adamw_torch, train.p
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -68,18 +69,27 @@ class ShardedBucket:
     """One flat bf16 parameter buffer (the tensors' `.data` are views into it) + this rank's slice of the optimizer state."""
 
     def __init__(self, name: str, params: Sequence[Tuple[str, torch.nn.Parameter]], world: int, rank: int,
-                 grad_dtype=torch.bfloat16):
+                 grad_dtype=torch.bfloat16, symmetric: bool = False):
+        """symmetric=True (world > 1): the flat parameter buffer is allocated as SYMMETRIC memory (same virtual layout on
+        every rank, mapped into every peer over NVLink, with an NVSwitch multicast address when the fabric has NVLS) so
+        that the optimizer kernel can write its updated slice into all replicas itself (`mm_adamw_step_bcast`)."""
         self.name, self.world, self.rank = name, world, rank
+        self.symm = None
         self.names = [n for n, _ in params]
         self.shapes = [tuple(p.shape) for _, p in params]
         self.sizes = [p.numel() for _, p in params]
         self.numel = sum(self.sizes)
         self.grad_dtype = grad_dtype
         dev = params[0][1].device
-        if len(params) == 1 and params[0][1].data.is_contiguous():
+        if len(params) == 1 and params[0][1].data.is_contiguous() and not (symmetric and world > 1):
             self.flat = params[0][1].data.view(-1)                       # a single tensor is its own flat buffer
         else:
-            self.flat = torch.empty(self.numel, dtype=torch.bfloat16, device=dev)
+            if symmetric and world > 1:
+                import torch.distributed._symmetric_memory as symm_mem
+                self.flat = symm_mem.empty(self.numel, dtype=torch.bfloat16, device=dev)
+                self.symm = symm_mem.rendezvous(self.flat, dist.group.WORLD)          # collective: same order on all ranks
+            else:
+                self.flat = torch.empty(self.numel, dtype=torch.bfloat16, device=dev)
             off = 0
             for (_, p), n in zip(params, self.sizes):
                 self.flat[off:off + n].copy_(p.data.reshape(-1))
@@ -124,11 +134,16 @@ def bucket_reduce(b: ShardedBucket, flat_grad: torch.Tensor, world: int) -> torc
     return b.gshard
 
 
-def bucket_update(b: ShardedBucket, gslice: torch.Tensor, adamw) -> None:
+def bucket_update(b: ShardedBucket, gslice: torch.Tensor, adamw, adamw_bcast=None) -> None:
     """`adamw(p16_out, p32, m, v, grad)` on this rank's slice; the updated bf16 slice then reaches every rank's flat
-    parameter buffer through the all-gather."""
+    parameter buffer — written there by the optimizer kernel itself when the bucket lives in symmetric memory
+    (`adamw_bcast(bucket, p32, m, v, grad)`: AdamW + all-gather in ONE kernel over NVSwitch multicast / NVLink P2P), else
+    through an NCCL all-gather."""
     if b.world == 1:
         adamw(b.flat, b.p32, b.m, b.v, gslice)
+        return
+    if b.symm is not None and adamw_bcast is not None:
+        adamw_bcast(b, b.p32, b.m, b.v, gslice)
         return
     adamw(b.pshard, b.p32, b.m, b.v, gslice)
     dist.all_gather_into_tensor(b.flat, b.pshard)
@@ -217,7 +232,7 @@ class TrainEngine:
                  weight_decay: float = 0.0, max_grad_norm: Optional[float] = None, total_steps: int = 1000,
                  warmup_ratio: float = 0.03, constant_lr: bool = False, n_save_gu_layers: int = 0,
                  pack_sequences: bool = False, pack_len: Optional[int] = None,
-                 gradient_accumulation_steps: int = 1, shard_optimizer: bool = True):
+                 gradient_accumulation_steps: int = 1, shard_optimizer: bool = True, fused_allgather: bool = True):
         self.model = model
         self.hot = HotPath(model)
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
@@ -234,6 +249,22 @@ class TrainEngine:
         # reduce-scatter + all-gather): the round-1 behaviour, kept for A/B measurements
         self.shard_world = self.world if shard_optimizer else 1
         self.shard_rank = self.rank if shard_optimizer else 0
+        # sharded state: fuse the all-gather of the updated parameters into the AdamW kernel (symmetric-memory buckets);
+        # falls back to NCCL all-gather if symmetric memory cannot be set up on this system
+        self.fused_allgather = bool(fused_allgather and self.shard_world > 1)
+        self.use_multicast = os.environ.get("MM_ADAMW_MULTICAST", "1") != "0"     # 0: per-peer P2P stores (A/B, debugging)
+        if self.fused_allgather:
+            try:
+                import torch.distributed._symmetric_memory as symm_mem   # noqa: F401
+                probe = symm_mem.empty(1024, dtype=torch.bfloat16, device=model.device)
+                symm_mem.rendezvous(probe, dist.group.WORLD)
+            except Exception as e:  # noqa: BLE001
+                import warnings
+                warnings.warn(f"symmetric memory unavailable ({type(e).__name__}: {e}); using NCCL all-gather")
+                self.fused_allgather = False
+            flag = torch.tensor([1 if self.fused_allgather else 0], device=model.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)           # every rank must take the same path
+            self.fused_allgather = bool(int(flag))
         self.named_params: Dict[str, torch.nn.Parameter] = dict(model.named_parameters())
         trainable = {n: p for n, p in self.named_params.items()
                      if p.requires_grad and "vision_tower" not in n and "vision_proj" not in n}
@@ -251,12 +282,14 @@ class TrainEngine:
                 p = f"model.layers.{i}."
                 names = [p + "self_attn.qkv_proj.weight", p + "self_attn.o_proj.weight", p + "mlp.gate_up_proj.weight",
                          p + "mlp.down_proj.weight"]
-                b = ShardedBucket(f"layer{i}", [(n, trainable[n]) for n in names], self.shard_world, self.shard_rank)
+                b = ShardedBucket(f"layer{i}", [(n, trainable[n]) for n in names], self.shard_world, self.shard_rank,
+                                  symmetric=self.fused_allgather)
                 self.layer_buckets.append(b)
                 claimed.update(names)
         for n, gd in (("lm_head.weight", torch.float32), ("model.embed_tokens.weight", torch.bfloat16)):
             if n in trainable and trainable[n].numel() % (8 * self.shard_world) == 0 and trainable[n].numel() >= (1 << 22):
-                self.big_buckets[n] = ShardedBucket(n, [(n, trainable[n])], self.shard_world, self.shard_rank, grad_dtype=gd)
+                self.big_buckets[n] = ShardedBucket(n, [(n, trainable[n])], self.shard_world, self.shard_rank, grad_dtype=gd,
+                                                    symmetric=self.fused_allgather)
                 claimed.add(n)
         for n, p in trainable.items():
             if n not in claimed:
@@ -274,6 +307,8 @@ class TrainEngine:
         # side stream: the gradient collectives (N > 1) and the HBM-bound fused AdamW run here, concurrently with the
         # tensor-core-bound backward GEMMs of the next layers on the main stream
         self.comm_stream = torch.cuda.Stream()
+        self._bcast_pending = False
+        self._fence = torch.zeros(1, dtype=torch.float32, device=model.device)
         resident = self.accum > 1 or max_grad_norm is not None
         self.provider = BucketGradProvider(model, self, resident=resident)
         self.provider.defer = max_grad_norm is not None
@@ -315,7 +350,30 @@ class TrainEngine:
 
     def _bucket_update(self, b: ShardedBucket, gslice, lr, grad_scale, scale_tensor=None):
         """(comm stream) fused AdamW on the slice, then the updated bf16 slice goes back into every rank's flat buffer."""
-        bucket_update(b, gslice, lambda p16, p32, m, v, g: self._adamw(p16, p32, m, v, g, lr, grad_scale, scale_tensor))
+        bucket_update(b, gslice, lambda p16, p32, m, v, g: self._adamw(p16, p32, m, v, g, lr, grad_scale, scale_tensor),
+                      (lambda bk, p32, m, v, g: self._adamw_bcast(bk, p32, m, v, g, lr, grad_scale, scale_tensor))
+                      if self.fused_allgather else None)
+        self._bcast_pending = self._bcast_pending or (self.fused_allgather and b.symm is not None)
+
+    def _adamw_bcast(self, b: ShardedBucket, p32, m, v, grad, lr, grad_scale, scale_tensor=None):
+        """AdamW on the slice; the kernel writes the updated bf16 values into every rank's replica of the bucket."""
+        b1, b2 = self.betas
+        h = b.symm
+        mc = int(h.multicast_ptr or 0)        # 0 when the fabric has no multicast (NVLS) support: per-peer stores instead
+        if not self.use_multicast:
+            mc = 0
+        ops.adamw_step_bcast_(mc + 2 * b.lo if mc else 0, int(h.buffer_ptrs_dev), self.shard_world, b.lo, p32.reshape(-1),
+                              m.reshape(-1), v.reshape(-1), grad.reshape(-1), lr=lr, beta1=b1, beta2=b2, eps=self.eps,
+                              wd=self.wd, step=self.step_count, grad_scale=grad_scale, grad_scale_tensor=scale_tensor)
+
+    def _fence_broadcasts(self):
+        """The kernels of THIS rank are ordered by its streams; the slices the PEERS write into this rank's buffers are
+        ordered by one tiny NCCL all-reduce at the end of the step's side-stream work: it cannot complete here before
+        every rank has finished the broadcast kernels it enqueued ahead of it."""
+        if self._bcast_pending:
+            with torch.cuda.stream(self.comm_stream):
+                dist.all_reduce(self._fence, op=dist.ReduceOp.SUM)
+            self._bcast_pending = False
 
     def reduce_and_apply(self, bucket: Optional[ShardedBucket], flat_grad, small_params, small_bufs):
         """Collective + AdamW of one completed bucket (and/or of small replicated tensors) on the side stream.
@@ -391,6 +449,7 @@ class TrainEngine:
         tot = tot / len(micro)
         if self.max_grad_norm is not None:
             self._clipped_update()
+        self._fence_broadcasts()
         torch.cuda.current_stream().wait_stream(self.comm_stream)
         self.last_tokens = tokens
         return dict(loss=tot[0], loss_language=tot[1:2], loss_image_ar=tot[2:3], tokens=tokens)

@@ -21,7 +21,7 @@ def _halves():
     return out
 
 
-def _rank_main(rank, world, init_file, out_dir, shard):
+def _rank_main(rank, world, init_file, out_dir, shard, fused):
     import torch.distributed as dist
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", init_method=f"file://{init_file}", rank=rank, world_size=world,
@@ -30,21 +30,28 @@ def _rank_main(rank, world, init_file, out_dir, shard):
     from oracle.weights import TINY, make_weights
     from tests.helpers import build_product_model
     model = build_product_model(TINY, make_weights(TINY), device=f"cuda:{rank}")
-    eng = TrainEngine(model, lr=1e-3, constant_lr=True, shard_optimizer=shard)
+    eng = TrainEngine(model, lr=1e-3, constant_lr=True, shard_optimizer=shard, fused_allgather=fused)
     assert eng.world == 2 and eng.shard_world == (2 if shard else 1)
+    if fused:
+        assert eng.fused_allgather, "symmetric memory / fused all-gather could not be set up on this box"
+        assert all(b.symm is not None for b in eng.layer_buckets)
     halves = _halves()
     for _ in range(2):
         out = eng.step(halves[rank])
     torch.cuda.synchronize()
     sd = {n: p.detach().float().cpu() for n, p in model.named_parameters() if p.requires_grad}
-    torch.save(dict(params=sd, loss=float(out["loss"]), state_bytes=eng.optimizer_state_bytes()),
+    mc = bool(eng.fused_allgather and int(eng.layer_buckets[0].symm.multicast_ptr or 0))
+    torch.save(dict(params=sd, loss=float(out["loss"]), state_bytes=eng.optimizer_state_bytes(), multicast=mc),
                os.path.join(out_dir, f"rank{rank}_{int(shard)}.pt"))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("shard", [True, False])
-def test_two_rank_step_equals_one_rank_accumulated_step(cuda_device, shard):
+@pytest.mark.parametrize("shard,fused", [(True, True), (True, False), (False, False)])
+def test_two_rank_step_equals_one_rank_accumulated_step(cuda_device, shard, fused):
+    """shard + fused: reduce-scatter -> ONE kernel doing AdamW on the slice and the all-gather (multimem.st through the
+    NVSwitch multicast address of the symmetric parameter buffer, or P2P stores); shard only: NCCL all-gather;
+    neither: replicated optimizer with an all-reduce."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     import torch.multiprocessing as mp
@@ -52,7 +59,7 @@ def test_two_rank_step_equals_one_rank_accumulated_step(cuda_device, shard):
     from oracle.weights import TINY, make_weights
     from tests.helpers import build_product_model
     with tempfile.TemporaryDirectory() as d:
-        mp.spawn(_rank_main, args=(2, os.path.join(d, "init"), d, shard), nprocs=2, join=True)
+        mp.spawn(_rank_main, args=(2, os.path.join(d, "init"), d, shard, fused), nprocs=2, join=True)
         r0 = torch.load(os.path.join(d, f"rank0_{int(shard)}.pt"))
         r1 = torch.load(os.path.join(d, f"rank1_{int(shard)}.pt"))
     for n in r0["params"]:                                     # the replicas stay bit-identical
@@ -65,6 +72,8 @@ def test_two_rank_step_equals_one_rank_accumulated_step(cuda_device, shard):
     torch.cuda.synchronize()
     if shard:
         assert r0["state_bytes"] < 0.55 * eng.optimizer_state_bytes()       # the big buckets hold half of the state
+    if fused:
+        print(f"[nccl] fused AdamW + all-gather ran with {'NVSwitch multicast (multimem.st)' if r0['multicast'] else 'per-peer P2P stores'}")
     assert abs(out["loss"].item() - 0.5 * (r0["loss"] + r1["loss"])) < 2e-3
     for n, p in model.named_parameters():
         if not p.requires_grad or "vision_proj" in n:
