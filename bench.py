@@ -563,7 +563,8 @@ def main():
                            "l2_policy": "inputs+weights (>100 GB/step) far exceed the 126 MB L2; no flush needed",
                            "max_grad_norm": None,
                            "optimizer": "AdamW fused into the backward sweep, fp32 master/m/v " +
-                                        ((f"sharded over the {world} ranks (ZeRO-1: reduce-scatter -> AdamW on the slice, "
+                                        ((f"sharded over the {world} ranks (ZeRO-1: " + ("" if getattr(engine, "fused_reduce", False) else "NCCL reduce-scatter -> ") + "AdamW on the slice, "
+                                          + ("IN-SWITCH gradient sum (multimem.ld_reduce) + " if getattr(engine, "fused_reduce", False) else "")
                                           + ("the same kernel broadcasts the updated slice into every replica (symmetric memory"
                                              + (", NVSwitch multicast)" if engine.fused_allgather and int(engine.layer_buckets[0].symm.multicast_ptr or 0) and engine.use_multicast else ", P2P stores)")
                                              if engine.fused_allgather else "-> NCCL all-gather") + ")")

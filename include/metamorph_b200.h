@@ -94,11 +94,15 @@ int mm_adamw_step(void* p16, float* p32, float* m, float* v, const void* grad, i
  * into EVERY rank's replica of the parameter buffer by the same kernel — through the NVSwitch multicast address of the
  * (symmetric) buffer (multimem.st) when multicast_p16 != NULL, else with one store per peer over NVLink P2P (peers = device
  * array of the n_peers buffer base pointers, slice_offset = first element of the slice). Replaces DeepSpeed ZeRO's
- * all-gather of updated parameters (scripts/zero2.json `allgather_bucket_size`). */
+ * all-gather of updated parameters (scripts/zero2.json `allgather_bucket_size`).
+ * grad_multicast = 1: `grad` is the multicast address of this rank's slice of the SYMMETRIC gradient buffers and is read
+ * with multimem.ld_reduce (sum over all ranks inside the switch, fp32 accumulation): the reduce-scatter is fused in as
+ * well, the bucket's whole [reduce-scatter -> AdamW -> all-gather] is one kernel (callers order it between two cross-rank
+ * barriers: every rank's gradients complete before, every rank done reading after). */
 int mm_adamw_step_bcast(void* multicast_p16, const void* const* peers, int n_peers, long long slice_offset, float* p32,
-                        float* m, float* v, const void* grad, int grad_f32, long long n, float lr, float beta1,
-                        float beta2, float eps, float wd, int step, const float* grad_scale_ptr, float grad_scale,
-                        cudaStream_t s);
+                        float* m, float* v, const void* grad, int grad_f32, int grad_multicast, long long n, float lr,
+                        float beta1, float beta2, float eps, float wd, int step, const float* grad_scale_ptr,
+                        float grad_scale, cudaStream_t s);
 int mm_clip_coef(const float* sumsq, float* out2, float max_norm, cudaStream_t s);
 
 /* Attention: LLaMA causal GQA (modeling_llama.py:199-220) forward/backward, SigLIP MHA forward

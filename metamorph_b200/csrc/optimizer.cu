@@ -12,7 +12,11 @@ namespace {
 // the same kernel (the all-gather of a sharded-optimizer step fused into the optimizer): one multimem.st through the
 // NVSwitch multicast mapping of the symmetric buffer when the fabric offers it (NVLS), else one st.global per peer over
 // NVLink P2P. The compute step (AdamW on this rank's slice) and its collective (all-gather of the slice) are ONE kernel.
-template <bool GRAD_F32, bool BCAST>
+// GRAD_MC (with BCAST): `grad` is the MULTICAST address of this rank's slice of the symmetric gradient buffers: one
+// multimem.ld_reduce returns the SUM over all ranks' buffers, added inside the NVSwitch (NVLS) with fp32 accumulation — the
+// reduce-scatter of the data-parallel step without a collective kernel. With both flags the whole
+// [reduce-scatter -> AdamW -> all-gather] of a parameter bucket is this ONE kernel.
+template <bool GRAD_F32, bool BCAST, bool GRAD_MC = false>
 __global__ void adamw_kernel(bf16* __restrict__ p16, float* __restrict__ p32, float* __restrict__ m,
                              float* __restrict__ v, const void* __restrict__ grad, long long n4,
                              float lr, float b1, float b2, float eps, float wd, float c1,
@@ -24,7 +28,20 @@ __global__ void adamw_kernel(bf16* __restrict__ p16, float* __restrict__ p32, fl
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
     float g[4];
-    if (GRAD_F32) {
+    if (GRAD_MC && GRAD_F32) {
+      asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(g[0]), "=f"(g[1]), "=f"(g[2]), "=f"(g[3])
+                   : "l"(reinterpret_cast<const float*>(grad) + i * 4)
+                   : "memory");
+    } else if (GRAD_MC) {
+      uint32_t u0, u1;
+      asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v2.bf16x2 {%0, %1}, [%2];"
+                   : "=r"(u0), "=r"(u1)
+                   : "l"(reinterpret_cast<const bf16*>(grad) + i * 4)
+                   : "memory");
+      const float2 a = unpack_bf16x2(u0), b = unpack_bf16x2(u1);
+      g[0] = a.x; g[1] = a.y; g[2] = b.x; g[3] = b.y;
+    } else if (GRAD_F32) {
       const float4 t = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(grad) + i * 4);
       g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w;
     } else {
@@ -102,9 +119,11 @@ MM_API int mm_adamw_step(void* p16, float* p32, float* m, float* v, const void* 
 // multicast_p16 != NULL: the multicast (NVLS) address of the slice; else peers = DEVICE array of n_peers buffer base
 // pointers and slice_offset = first element of the slice inside each of them.
 MM_API int mm_adamw_step_bcast(void* multicast_p16, const void* const* peers, int n_peers, long long slice_offset,
-                               float* p32, float* m, float* v, const void* grad, int grad_f32, long long n, float lr,
-                               float beta1, float beta2, float eps, float wd, int step, const float* grad_scale_ptr,
-                               float grad_scale, cudaStream_t stream) {
+                               float* p32, float* m, float* v, const void* grad, int grad_f32, int grad_multicast,
+                               long long n, float lr, float beta1, float beta2, float eps, float wd, int step,
+                               const float* grad_scale_ptr, float grad_scale, cudaStream_t stream) {
+  MM_CHECK_ARG(!grad_multicast || multicast_p16 != nullptr,
+               "mm_adamw_step_bcast: the in-switch gradient reduction needs the multicast parameter address as well");
   MM_CHECK_ARG(n > 0 && n % 4 == 0 && slice_offset % 4 == 0, "mm_adamw_step_bcast: n / offset must be multiples of 4");
   MM_CHECK_ARG(step >= 1, "mm_adamw_step_bcast: step starts at 1");
   MM_CHECK_ARG(multicast_p16 != nullptr || (peers != nullptr && n_peers > 0), "mm_adamw_step_bcast: no destination");
@@ -116,12 +135,14 @@ MM_API int mm_adamw_step_bcast(void* multicast_p16, const void* const* peers, in
   if (blocks > cap) blocks = cap;
   bf16* dst = multicast_p16 ? (bf16*)multicast_p16 : reinterpret_cast<bf16*>(slice_offset * 2);   // address or byte offset
   bf16* const* pr = multicast_p16 ? nullptr : (bf16* const*)peers;
-  if (grad_f32)
-    adamw_kernel<true, true><<<(int)blocks, 256, 0, stream>>>(dst, p32, m, v, grad, n4, lr, beta1, beta2, eps, wd, c1, sqrt_c2,
-                                                              grad_scale_ptr, grad_scale, pr, n_peers);
-  else
-    adamw_kernel<false, true><<<(int)blocks, 256, 0, stream>>>(dst, p32, m, v, grad, n4, lr, beta1, beta2, eps, wd, c1,
-                                                               sqrt_c2, grad_scale_ptr, grad_scale, pr, n_peers);
+#define MM_ADAMW_B(F32, MC)                                                                                          \
+  adamw_kernel<F32, true, MC><<<(int)blocks, 256, 0, stream>>>(dst, p32, m, v, grad, n4, lr, beta1, beta2, eps, wd, c1, \
+                                                               sqrt_c2, grad_scale_ptr, grad_scale, pr, n_peers)
+  if (grad_f32 && grad_multicast) MM_ADAMW_B(true, true);
+  else if (grad_f32) MM_ADAMW_B(true, false);
+  else if (grad_multicast) MM_ADAMW_B(false, true);
+  else MM_ADAMW_B(false, false);
+#undef MM_ADAMW_B
   MM_CHECK_LAUNCH();
   return MM_OK;
 }

@@ -100,9 +100,22 @@ class ShardedBucket:
         self.p32 = sl.float()
         self.m = torch.zeros_like(self.p32)
         self.v = torch.zeros_like(self.p32)
-        # staging for the collectives (world > 1): the reduced gradient slice and the updated bf16 slice
-        self.gshard = torch.empty(self.hi - self.lo, dtype=grad_dtype, device=dev) if world > 1 else None
-        self.pshard = torch.empty(self.hi - self.lo, dtype=torch.bfloat16, device=dev) if world > 1 else None
+        # staging of the NCCL path (world > 1): the reduced gradient slice and the updated bf16 slice, allocated on first
+        # use (the fused NVSwitch path needs neither)
+        self._gshard = self._pshard = None
+
+    @property
+    def gshard(self) -> torch.Tensor:
+        if self._gshard is None:
+            self._gshard = torch.empty(self.hi - self.lo, dtype=self.grad_dtype, device=self.flat.device)
+        return self._gshard
+
+    @property
+    def pshard(self) -> torch.Tensor:
+        if self._pshard is None:
+            self._pshard = torch.empty(self.hi - self.lo, dtype=torch.bfloat16, device=self.flat.device)
+        return self._pshard
+
 
     def param_views(self) -> Dict[str, _OptState]:
         """Per-tensor views of the state for tensors that lie entirely inside this rank's slice."""
@@ -149,6 +162,13 @@ def bucket_update(b: ShardedBucket, gslice: torch.Tensor, adamw, adamw_bcast=Non
     dist.all_gather_into_tensor(b.flat, b.pshard)
 
 
+def probe_hdl_multicast(device) -> int:
+    """Multicast (NVLS) address of a scratch symmetric allocation, 0 when the fabric has none. Collective."""
+    import torch.distributed._symmetric_memory as symm_mem
+    t = symm_mem.empty(1024, dtype=torch.bfloat16, device=device)
+    return int(symm_mem.rendezvous(t, dist.group.WORLD).multicast_ptr or 0)
+
+
 class BucketGradProvider(GradProvider):
     """Hands the hot path its gradient destinations and fires a bucket's collective + AdamW as soon as it is complete.
 
@@ -167,11 +187,24 @@ class BucketGradProvider(GradProvider):
         dev = model.device
         if lb:
             n_sets = len(lb) if resident else min(2, len(lb))
-            self.sets = [dict(flat=torch.zeros(lb[0].numel, dtype=torch.bfloat16, device=dev),
-                              ln=torch.zeros(2 * self.H, dtype=torch.float32, device=dev), free=None)
-                         for _ in range(n_sets)]
+            self.sets = []
+            for _ in range(n_sets):
+                flat, hdl = engine.alloc_grad(lb[0].numel, torch.bfloat16)
+                self.sets.append(dict(flat=flat, hdl=hdl, ln=torch.zeros(2 * self.H, dtype=torch.float32, device=dev),
+                                      free=None))
         else:
             self.sets = []
+        self.big_hdl: Dict[str, object] = {}       # symmetric-memory handles of the lm_head / embedding gradient buffers
+
+    def get(self, name: str, like: torch.Tensor, fp32: bool = False, zero: bool = False) -> torch.Tensor:
+        if name in self.e.big_buckets and name not in self.buffers and self.e.fused_reduce:
+            # the gradient of a sharded big tensor lives in symmetric memory: its slice is summed over the ranks inside
+            # the switch by the optimizer kernel (collective allocation: every rank reaches this point in the same step)
+            flat, hdl = self.e.alloc_grad(like.numel(), torch.float32 if fp32 else like.dtype)
+            self.buffers[name] = flat.view(like.shape)
+            self.big_hdl[name] = hdl
+            return self.buffers[name]
+        return super().get(name, like, fp32=fp32, zero=zero)
 
     def _set(self, i: int):
         return self.sets[i if self.resident else i % len(self.sets)]
@@ -195,7 +228,7 @@ class BucketGradProvider(GradProvider):
         if self.defer:
             self.pending.append((self.e.layer_buckets[i], s["flat"], small, [s["ln"]]))
             return
-        s["free"] = self.e.reduce_and_apply(self.e.layer_buckets[i], s["flat"], small, [s["ln"]])
+        s["free"] = self.e.reduce_and_apply(self.e.layer_buckets[i], s["flat"], small, [s["ln"]], grad_hdl=s["hdl"])
 
     GROUPS = {
         "heads": ["lm_head.weight", "vision_head.0.weight", "vision_head.0.bias", "vision_head.2.weight",
@@ -216,6 +249,10 @@ class BucketGradProvider(GradProvider):
         named = self.e.named_params
         for n in names:
             if n in self.e.big_buckets:
+                if not self.defer:
+                    self.e.reduce_and_apply(self.e.big_buckets[n], self.buffers[n].view(-1), [], [],
+                                            grad_hdl=self.big_hdl.get(n))
+                    continue
                 item = (self.e.big_buckets[n], self.buffers[n].view(-1), [], [])
             elif n in self.e.small_state:
                 item = (None, None, [(named[n], self.buffers[n])], [self.buffers[n]])
@@ -265,6 +302,15 @@ class TrainEngine:
             flag = torch.tensor([1 if self.fused_allgather else 0], device=model.device)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)           # every rank must take the same path
             self.fused_allgather = bool(int(flag))
+        # ... and the reduce-scatter too: gradients in symmetric memory, summed over the ranks INSIDE the NVSwitch by the
+        # optimizer kernel's multimem.ld_reduce -> a bucket's [reduce-scatter -> AdamW -> all-gather] is one kernel and
+        # NCCL leaves the data path (needs multicast/NVLS support; not used with clipping, which needs the slice norms first)
+        self.fused_reduce = bool(self.fused_allgather and self.use_multicast and max_grad_norm is None and
+                                 os.environ.get("MM_FUSED_REDUCE", "1") != "0")
+        if self.fused_reduce:
+            has_mc = torch.tensor([1 if int(probe_hdl_multicast(model.device)) else 0], device=model.device)
+            dist.all_reduce(has_mc, op=dist.ReduceOp.MIN)
+            self.fused_reduce = bool(int(has_mc))
         self.named_params: Dict[str, torch.nn.Parameter] = dict(model.named_parameters())
         trainable = {n: p for n, p in self.named_params.items()
                      if p.requires_grad and "vision_tower" not in n and "vision_proj" not in n}
@@ -315,6 +361,17 @@ class TrainEngine:
         self.kernel_launch_estimate = 0
 
     # -------------------------------------------------------------- optimizer plumbing
+    def alloc_grad(self, numel: int, dtype):
+        """A zeroed flat gradient buffer: symmetric memory (+ its handle) when the reduction is fused into the optimizer
+        kernel, plain device memory otherwise. Collective in the symmetric case."""
+        dev = self.model.device
+        if not self.fused_reduce:
+            return torch.zeros(numel, dtype=dtype, device=dev), None
+        import torch.distributed._symmetric_memory as symm_mem
+        t = symm_mem.empty(numel, dtype=dtype, device=dev)
+        t.zero_()
+        return t, symm_mem.rendezvous(t, dist.group.WORLD)
+
     def optimizer_state_bytes(self) -> int:
         n = sum(b.p32.numel() for b in list(self.layer_buckets) + list(self.big_buckets.values()))
         n += sum(st.p32.numel() for st in self.small_state.values())
@@ -375,7 +432,7 @@ class TrainEngine:
                 dist.all_reduce(self._fence, op=dist.ReduceOp.SUM)
             self._bcast_pending = False
 
-    def reduce_and_apply(self, bucket: Optional[ShardedBucket], flat_grad, small_params, small_bufs):
+    def reduce_and_apply(self, bucket: Optional[ShardedBucket], flat_grad, small_params, small_bufs, grad_hdl=None):
         """Collective + AdamW of one completed bucket (and/or of small replicated tensors) on the side stream.
         Returns an event marking when the gradient buffers may be reused."""
         lr = self.current_lr
@@ -384,7 +441,21 @@ class TrainEngine:
         ready.record()
         with torch.cuda.stream(self.comm_stream):
             self.comm_stream.wait_event(ready)
-            if bucket is not None:
+            if bucket is not None and self.fused_reduce and grad_hdl is not None and bucket.symm is not None:
+                # ONE kernel per bucket: in-switch sum of every rank's gradient slice (multimem.ld_reduce) -> AdamW ->
+                # broadcast of the updated bf16 slice (multimem.st). Two cross-rank barriers order it: all ranks have
+                # written their gradients / all ranks have read them (the buffer is reused two layers later).
+                grad_hdl.barrier(channel=0)
+                b1, b2 = self.betas
+                esz = flat_grad.element_size()
+                ops.adamw_step_bcast_(int(bucket.symm.multicast_ptr) + 2 * bucket.lo, 0, self.shard_world, bucket.lo,
+                                      bucket.p32.reshape(-1), bucket.m.reshape(-1), bucket.v.reshape(-1), None, lr=lr,
+                                      beta1=b1, beta2=b2, eps=self.eps, wd=self.wd, step=self.step_count, grad_scale=scale,
+                                      grad_multicast_ptr=int(grad_hdl.multicast_ptr) + esz * bucket.lo,
+                                      grad_f32=(flat_grad.dtype == torch.float32))
+                grad_hdl.barrier(channel=1)
+                self._bcast_pending = True
+            elif bucket is not None:
                 g = self._bucket_reduce(bucket, flat_grad)
                 self._bucket_update(bucket, g, lr, scale)
             if small_params:

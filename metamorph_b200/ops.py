@@ -285,14 +285,22 @@ def adamw_step_(p16, p32, m, v, grad, *, lr, beta1, beta2, eps, wd, step, grad_s
 
 
 def adamw_step_bcast_(multicast_ptr, peers_dev_ptr, n_peers, slice_offset, p32, m, v, grad, *, lr, beta1, beta2, eps, wd, step,
-                      grad_scale=1.0, grad_scale_tensor=None):
+                      grad_scale=1.0, grad_scale_tensor=None, grad_multicast_ptr=0, grad_f32=None):
     """AdamW on this rank's slice with the all-gather fused in (csrc/optimizer.cu): the updated bf16 values go straight
-    into every rank's parameter buffer (multicast address of the slice, or per-peer stores)."""
-    require_cuda(p32, m, v, grad)
+    into every rank's parameter buffer (multicast address of the slice, or per-peer stores).
+    grad_multicast_ptr != 0: the gradient is read through that multicast address (multimem.ld_reduce = the sum over all
+    ranks' symmetric gradient buffers, formed inside the NVSwitch): reduce-scatter fused in as well (`grad` is ignored)."""
+    require_cuda(p32, m, v)
     n = p32.numel()
-    assert m.numel() == n and v.numel() == n and grad.numel() == n and grad.is_contiguous()
+    assert m.numel() == n and v.numel() == n
+    if grad_multicast_ptr:
+        g_ptr, g_f32 = c_void_p(grad_multicast_ptr), bool(grad_f32)
+    else:
+        require_cuda(grad)
+        assert grad.numel() == n and grad.is_contiguous()
+        g_ptr, g_f32 = ptr(grad), grad.dtype == torch.float32
     call("mm_adamw_step_bcast", c_void_p(multicast_ptr or 0), c_void_p(peers_dev_ptr or 0), c_int(n_peers), ll(slice_offset),
-         ptr(p32), ptr(m), ptr(v), ptr(grad), c_int(1 if grad.dtype == torch.float32 else 0), ll(n), c_float(lr),
+         ptr(p32), ptr(m), ptr(v), g_ptr, c_int(int(g_f32)), c_int(1 if grad_multicast_ptr else 0), ll(n), c_float(lr),
          c_float(beta1), c_float(beta2), c_float(eps), c_float(wd), c_int(step), ptr(grad_scale_tensor),
          c_float(grad_scale), stream_ptr())
 

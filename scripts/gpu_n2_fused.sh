@@ -5,8 +5,8 @@ TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 
 timeout 500 python -m pytest tests/test_dp_nccl_gpu.py -m gpu -q -rs -s > $o/r02_nccl_test2.log 2>&1
 tail -12 $o/r02_nccl_test2.log | cut -c1-300
 timeout 400 $TR --master-port 29521 bench.py --gpus 2 --steps 6 --warmup 3 > $o/r02_bench_n2_fused.json 2> $o/r02_bench_n2_fused.err
-timeout 400 $TR --master-port 29522 bench.py --gpus 2 --steps 6 --warmup 3 --no-fused-allgather > $o/r02_bench_n2_nccl_ag.json 2> $o/r02_bench_n2_nccl_ag.err
-for f in r02_bench_n2_fused r02_bench_n2_nccl_ag; do python - "$o/$f.json" <<'PY'
+MM_FUSED_REDUCE=0 timeout 400 $TR --master-port 29522 bench.py --gpus 2 --steps 6 --warmup 3 > $o/r02_bench_n2_fused_ag_only.json 2> $o/r02_bench_n2_fused_ag_only.err
+for f in r02_bench_n2_fused r02_bench_n2_fused_ag_only; do python - "$o/$f.json" <<'PY'
 import json, sys
 try:
     d = json.load(open(sys.argv[1]))

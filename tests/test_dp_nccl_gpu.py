@@ -41,7 +41,8 @@ def _rank_main(rank, world, init_file, out_dir, shard, fused):
     torch.cuda.synchronize()
     sd = {n: p.detach().float().cpu() for n, p in model.named_parameters() if p.requires_grad}
     mc = bool(eng.fused_allgather and int(eng.layer_buckets[0].symm.multicast_ptr or 0))
-    torch.save(dict(params=sd, loss=float(out["loss"]), state_bytes=eng.optimizer_state_bytes(), multicast=mc),
+    torch.save(dict(params=sd, loss=float(out["loss"]), state_bytes=eng.optimizer_state_bytes(), multicast=mc,
+                    fused_reduce=bool(eng.fused_reduce)),
                os.path.join(out_dir, f"rank{rank}_{int(shard)}.pt"))
     dist.barrier()
     dist.destroy_process_group()
@@ -73,7 +74,8 @@ def test_two_rank_step_equals_one_rank_accumulated_step(cuda_device, shard, fuse
     if shard:
         assert r0["state_bytes"] < 0.55 * eng.optimizer_state_bytes()       # the big buckets hold half of the state
     if fused:
-        print(f"[nccl] fused AdamW + all-gather ran with {'NVSwitch multicast (multimem.st)' if r0['multicast'] else 'per-peer P2P stores'}")
+        print(f"[nccl] fused AdamW + all-gather ran with {'NVSwitch multicast (multimem.st)' if r0['multicast'] else 'per-peer P2P stores'}"
+              f"; reduce-scatter {'fused too (multimem.ld_reduce, in-switch sum)' if r0['fused_reduce'] else 'through NCCL'}")
     assert abs(out["loss"].item() - 0.5 * (r0["loss"] + r1["loss"])) < 2e-3
     for n, p in model.named_parameters():
         if not p.requires_grad or "vision_proj" in n:
