@@ -359,7 +359,7 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   const uint32_t bar = base + 6 * BW_TILE + 2048;
   const uint32_t kv_full = bar, qdo_full0 = bar + 8, qdo_full1 = bar + 16, qdo_empty0 = bar + 24,
                  qdo_empty1 = bar + 32, st_full = bar + 40, dp_full = bar + 48, p_full = bar + 56, ds_full = bar + 64,
-                 fin_full = bar + 72, tmem_slot = bar + 80;
+                 fin_full = bar + 72, tmem_slot = bar + 80, stat_empty0 = bar + 88, stat_empty1 = bar + 96;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + 6 * BW_TILE + 2048 + 80);
 
   if (warp == 0 && lane == 0) {
@@ -371,6 +371,8 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
     mbar_init(p_full, 16);
     mbar_init(ds_full, 16);
     mbar_init(fin_full, 1);
+    mbar_init(stat_empty0, 16);   // the 16 elementwise warps have read the lse2 / delta rows of this buffer
+    mbar_init(stat_empty1, 16);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -392,7 +394,10 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       const int hq = hk * G + it / n_qt;
       const int q0 = (qt_begin + it % n_qt) * 128;
       const uint32_t full = buf ? qdo_full1 : qdo_full0, empty = buf ? qdo_empty1 : qdo_empty0;
-      mbar_wait(empty, (uint32_t)((use & 1) ^ 1));
+      mbar_wait(empty, (uint32_t)((use & 1) ^ 1));          // the MMAs that read Q / dO of this buffer have completed
+      // The statistics rows are read by the elementwise warps (generic proxy): their own barrier orders the overwrite
+      // directly (it is also implied by ds_full -> MMA thread -> commit on `empty`, a chain racecheck cannot follow).
+      mbar_wait(buf ? stat_empty1 : stat_empty0, (uint32_t)((use & 1) ^ 1));
       mbar_arrive_expect_tx(full, 2 * BW_TILE + 1024);
       {
         const long long off = ((long long)b * p.Hq + hq) * p.Tp + q0;
@@ -532,7 +537,10 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       tmem_st_wait();
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(ds_full);
+      if (lane == 0) {
+        mbar_arrive(ds_full);
+        mbar_arrive(sbuf ? stat_empty1 : stat_empty0);
+      }
     }
     // ---- final: dK (already scaled through dS) and dV
     mbar_wait(fin_full, 0);

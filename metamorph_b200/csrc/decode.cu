@@ -2,12 +2,12 @@
 //
 // The reference re-runs the whole prefix every step with no cache (metamorph_llama.py:510,526-535);
 // the mathematically equivalent cached step is HBM-bound: every weight byte is streamed once per
-// step for <= 8 sequences. Kernels:
-//   skinny_gemm   y[m<=8, N] = x[m, K] * W[N, K]^T : weight-streaming with mma.sync m16n8k16 where
+// step for <= 32 sequences. Kernels:
+//   skinny_gemm   y[m<=32, N] = x[m, K] * W[N, K]^T : weight-streaming with mma.sync m16n8k16 where
 //                 the 16-row operand is a slab of W (rows = output features) and the 8-wide operand
-//                 is the batch. Each lane pulls 2 x 128-bit of W per k32 step straight from HBM in
-//                 fragment order (a k-permutation shared by both operands), 8 warps split K, fp32
-//                 cross-warp reduction in smem, fused bias / residual / GELU / SwiGLU epilogue.
+//                 is the batch (1, 2 or 4 n8 tiles). Weight slab and activation slice travel together
+//                 through a TMA ring, 4 consumer warps split K, fp32 cross-warp reduction in smem, fused
+//                 bias / residual / GELU / SwiGLU epilogue.
 //   decode_attn   per (sequence, kv head): RoPE on the new q (4 GQA heads) and k, append k/v to the
 //                 cache, single-query attention over the cache, all in one launch.
 //   decode_state  the per-sequence text/image mode state machine of greedy_decode
@@ -35,7 +35,7 @@ constexpr int SK2_STAGES = 8;      // default ring depth (16-row slabs: 8 x 8 KB
 constexpr int SK2_KT = 256;      // k elements per stage
 constexpr int SK2_THREADS = 160; // warp 0 = TMA producer, warps 1..4 = consumers
 
-template <int ROWS, int NST = SK2_STAGES>
+template <int ROWS, int NST = SK2_STAGES, int NB = 1>
 __global__ void __launch_bounds__(SK2_THREADS)
 skinny_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
                        void* __restrict__ y, long long ldy, const bf16* __restrict__ bias,
@@ -43,8 +43,9 @@ skinny_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
                        int pdl) {
   constexpr int G = ROWS >= 16 ? ROWS / 16 : 1;
   constexpr bool HALF = ROWS == 8;             // 8-row slab: rows 8..15 of the MMA operand are zero
+  constexpr int MB = 8 * NB;                   // batch rows served: NB n8 tiles of the MMA's B operand
   constexpr int BOX = ROWS * 128;              // bytes of one [ROWS x 64 k] weight box
-  constexpr int XBOX = 8 * 128;                // bytes of one [8 batch rows x 64 k] activation box
+  constexpr int XBOX = MB * 128;               // bytes of one [MB batch rows x 64 k] activation box
   constexpr int STAGE_W = 4 * BOX;             // 4 boxes = 256 k of the weight slab
   constexpr int STAGE = STAGE_W + 4 * XBOX;    // + the same 256 k of the activations (rows >= m zero-filled by TMA)
   extern __shared__ uint8_t smem_raw[];
@@ -52,7 +53,7 @@ skinny_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
   constexpr int BARB = (2 * NST * 8 + 127) & ~127;      // bytes of the full/empty barrier block
   const uint32_t bar = base + NST * STAGE;
-  float* red = reinterpret_cast<float*>(base_ptr + NST * STAGE + BARB);   // [4][ROWS][8]
+  float* red = reinterpret_cast<float*>(base_ptr + NST * STAGE + BARB);   // [4][ROWS][MB]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * ROWS;
   const int n_kt = (K + SK2_KT - 1) / SK2_KT;
@@ -103,11 +104,13 @@ skinny_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
   } else {
     const int cw = warp - 1;                 // consumer index 0..3
     const int g = lane >> 2, t = lane & 3;
-    float acc[G][4];
+    float acc[G][NB][4];
 #pragma unroll
     for (int i = 0; i < G; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+      for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][nb][j] = 0.f;
     for (int kt = 0; kt < n_kt; ++kt) {
       const int s = kt % NST;
       const uint32_t ph = (uint32_t)((kt / NST) & 1);
@@ -118,8 +121,12 @@ skinny_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
         const int cc = 2 * cw + u;             // k32 chunk of this stage: box cc/2, half cc%2
         const uint8_t* bx = st + (cc >> 1) * BOX;
         const int chunk = (cc & 1) * 4 + t;    // 16-byte chunk index inside the 128-byte row
-        // B fragment: batch row g, the same 8 k values (128-byte swizzled [8 x 64] box)
-        const int4 xb = *reinterpret_cast<const int4*>(st + STAGE_W + (cc >> 1) * XBOX + g * 128 + ((chunk ^ g) << 4));
+        // B fragments: batch rows g + 8 nb, the same 8 k values (128-byte swizzled [MB x 64] box; the swizzle repeats
+        // every 8 rows, so row g + 8 nb uses the same chunk permutation as row g)
+        int4 xb[NB];
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb)
+          xb[nb] = *reinterpret_cast<const int4*>(st + STAGE_W + (cc >> 1) * XBOX + (nb * 8 + g) * 128 + ((chunk ^ g) << 4));
 #pragma unroll
         for (int i = 0; i < G; ++i) {
           const int r0 = i * 16 + g, r1 = r0 + 8;
@@ -128,48 +135,56 @@ skinny_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
                                : *reinterpret_cast<const int4*>(bx + r1 * 128 + ((chunk ^ (r1 & 7)) << 4));
           const uint32_t a1[4] = {(uint32_t)w0.x, (uint32_t)w1.x, (uint32_t)w0.y, (uint32_t)w1.y};
           const uint32_t a2[4] = {(uint32_t)w0.z, (uint32_t)w1.z, (uint32_t)w0.w, (uint32_t)w1.w};
-          mma_bf16_16816(acc[i], a1, (uint32_t)xb.x, (uint32_t)xb.y);
-          mma_bf16_16816(acc[i], a2, (uint32_t)xb.z, (uint32_t)xb.w);
+#pragma unroll
+          for (int nb = 0; nb < NB; ++nb) {
+            mma_bf16_16816(acc[i][nb], a1, (uint32_t)xb[nb].x, (uint32_t)xb[nb].y);
+            mma_bf16_16816(acc[i][nb], a2, (uint32_t)xb[nb].z, (uint32_t)xb[nb].w);
+          }
         }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(bar + 8 * (NST + s));
     }
 #pragma unroll
-    for (int i = 0; i < G; ++i) {
-      red[(cw * ROWS + i * 16 + g) * 8 + 2 * t] = acc[i][0];
-      red[(cw * ROWS + i * 16 + g) * 8 + 2 * t + 1] = acc[i][1];
-      if (!HALF) {
-        red[(cw * ROWS + i * 16 + g + 8) * 8 + 2 * t] = acc[i][2];
-        red[(cw * ROWS + i * 16 + g + 8) * 8 + 2 * t + 1] = acc[i][3];
+    for (int i = 0; i < G; ++i)
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) {
+        float* rr = red + (cw * ROWS + i * 16 + g) * MB + nb * 8 + 2 * t;
+        rr[0] = acc[i][nb][0];
+        rr[1] = acc[i][nb][1];
+        if (!HALF) {
+          rr[8 * MB] = acc[i][nb][2];
+          rr[8 * MB + 1] = acc[i][nb][3];
+        }
       }
-    }
   }
   griddep_wait();
   __syncthreads();
   if (pdl & 8) griddep_launch();
   if (epi == SK_SWIGLU) {
-    if (ROWS == 32 && threadIdx.x < 128) {
-      const int r = threadIdx.x >> 3, b = threadIdx.x & 7;
-      float gsum = 0.f, usum = 0.f;
+    if (ROWS == 32) {
+      for (int idx = threadIdx.x; idx < 16 * MB; idx += SK2_THREADS) {
+        const int r = idx / MB, b = idx % MB;
+        float gsum = 0.f, usum = 0.f;
 #pragma unroll
-      for (int w = 0; w < 4; ++w) {
-        gsum += red[(w * ROWS + r) * 8 + b];
-        usum += red[(w * ROWS + r + 16) * 8 + b];
+        for (int w = 0; w < 4; ++w) {
+          gsum += red[(w * ROWS + r) * MB + b];
+          usum += red[(w * ROWS + r + 16) * MB + b];
+        }
+        const int col = (n0 >> 1) + r;
+        if (b < m && n0 + r < N)
+          reinterpret_cast<bf16*>(y)[(long long)b * ldy + col] = __float2bfloat16(silu(gsum) * usum);
       }
-      const int col = (n0 >> 1) + r;
-      if (b < m && n0 + r < N)
-        reinterpret_cast<bf16*>(y)[(long long)b * ldy + col] = __float2bfloat16(silu(gsum) * usum);
     }
     return;
   }
-  for (int idx = threadIdx.x; idx < ROWS * 8; idx += SK2_THREADS) {
-    const int r = idx >> 3, b = idx & 7;
+  for (int idx = threadIdx.x; idx < ROWS * MB; idx += SK2_THREADS) {
+    const int r = idx / MB, b = idx % MB;
     const int n = n0 + r;
     if (b >= m || n >= N) continue;
     float sacc = 0.f;
 #pragma unroll
-    for (int w = 0; w < 4; ++w) sacc += red[(w * ROWS + r) * 8 + b];
+    for (int w = 0; w < 4; ++w) sacc += red[(w * ROWS + r) * MB + b];
     if (epi == SK_BIAS || epi == SK_BIAS_GELU) sacc += __bfloat162float(bias[n]);
     if (epi == SK_BIAS_GELU) sacc = gelu_erf(sacc);
     if (epi == SK_RESID) sacc += __bfloat162float(resid[(long long)b * ldr + n]);
@@ -491,20 +506,21 @@ __global__ void decode_select_hidden_kernel(const int* __restrict__ mode, const 
 
 namespace {
 
-template <int ROWS, int NST>
+template <int ROWS, int NST, int NB>
 int launch_skinny_tma(const CUtensorMap& tw, const CUtensorMap& tx, void* y, long long ldy, const void* bias,
                       const void* resid, long long ldr, int m, int N, int K, int epilogue, int out_f32, int pm,
                       cudaStream_t stream) {
-  constexpr int smem = NST * (4 * ROWS * 128 + 4 * 8 * 128) + ((2 * NST * 8 + 127) & ~127) + 4 * ROWS * 8 * 4 + 1024;
+  constexpr int smem = NST * (4 * ROWS * 128 + 4 * 8 * NB * 128) + ((2 * NST * 8 + 127) & ~127) + 4 * ROWS * 8 * NB * 4 + 1024;
+  static_assert(smem <= 227 * 1024, "skinny GEMM ring does not fit in shared memory");
   static std::once_flag once;
   static cudaError_t err = cudaSuccess;
   std::call_once(once, [&] {
-    err = cudaFuncSetAttribute(skinny_gemm_tma_kernel<ROWS, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    err = cudaFuncSetAttribute(skinny_gemm_tma_kernel<ROWS, NST, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   });
   MM_CHECK_CUDA(err);
-  MM_CHECK_CUDA(launch_pdl(pm & 1, skinny_gemm_tma_kernel<ROWS, NST>, dim3((N + ROWS - 1) / ROWS), dim3(SK2_THREADS), smem,
-                           stream, tw, tx, y, ldy, (const bf16*)bias, (const bf16*)resid, ldr, m, N, K, epilogue, out_f32,
-                           pm));
+  MM_CHECK_CUDA(launch_pdl(pm & 1, skinny_gemm_tma_kernel<ROWS, NST, NB>, dim3((N + ROWS - 1) / ROWS), dim3(SK2_THREADS),
+                           smem, stream, tw, tx, y, ldy, (const bf16*)bias, (const bf16*)resid, ldr, m, N, K, epilogue,
+                           out_f32, pm));
   MM_CHECK_LAUNCH();
   return MM_OK;
 }
@@ -514,17 +530,19 @@ int launch_skinny_tma(const CUtensorMap& tw, const CUtensorMap& tx, void* y, lon
 MM_API int mm_skinny_gemm(const void* x, const void* W, void* y, const void* bias, const void* resid,
                           long long ldx, long long ldw, long long ldy, long long ldr, int m, int N,
                           int K, int epilogue, int out_f32, cudaStream_t stream) {
-  MM_CHECK_ARG(m >= 1 && m <= 8, "mm_skinny_gemm: batch must be in [1,8] (m=%d)", m);
+  MM_CHECK_ARG(m >= 1 && m <= 32, "mm_skinny_gemm: batch must be in [1,32] (m=%d)", m);
   MM_CHECK_ARG(K % 32 == 0 && ldx % 8 == 0 && ldw % 8 == 0, "mm_skinny_gemm: need K%%32==0, ldx/ldw%%8==0");
   MM_CHECK_ARG(((uintptr_t)W & 15) == 0 && ((uintptr_t)x & 15) == 0, "mm_skinny_gemm: x / W must be 16-byte aligned");
   MM_CHECK_ARG(epilogue >= SK_STORE && epilogue <= SK_SWIGLU, "mm_skinny_gemm: bad epilogue");
   MM_CHECK_ARG((epilogue != SK_BIAS && epilogue != SK_BIAS_GELU) || bias, "mm_skinny_gemm: bias missing");
   MM_CHECK_ARG(epilogue != SK_RESID || resid, "mm_skinny_gemm: residual missing");
   const int pm = mm_pdl_mode();
-  // 32-row slabs where the epilogue needs them (SwiGLU: 16 gate + 16 up rows of the same channels) and for very
-  // large N (lm_head: fewer, longer-lived CTAs); 16-row slabs otherwise
-  static const int rows_env = getenv("MM_SK2_ROWS") ? atoi(getenv("MM_SK2_ROWS")) : 0;   // experiments: 32 = 32-row slabs everywhere
-  const bool rows32 = (epilogue == SK_SWIGLU) || (N >= 32 * 4 * mm_num_sms()) || (rows_env == 32 && N % 32 == 0);
+  // The batch is the n dimension of the MMA: 1, 2 or 4 n8 tiles (8 / 16 / 32 sequences) share every weight fragment.
+  const int nb = m <= 8 ? 1 : (m <= 16 ? 2 : 4);
+  // 32-row slabs where the epilogue needs them (SwiGLU: 16 gate + 16 up rows of the same channels), for very large N
+  // (lm_head: fewer, longer-lived CTAs) and for 32 sequences (each CTA re-reads the whole activation block from L2: the
+  // taller slab halves that traffic); 16-row slabs otherwise
+  const bool rows32 = (epilogue == SK_SWIGLU) || (N >= 32 * 4 * mm_num_sms()) || nb == 4;
   if (epilogue == SK_SWIGLU) MM_CHECK_ARG(N % 32 == 0 && !out_f32, "mm_skinny_gemm: SWIGLU needs N%%32==0");
   static PFN_encodeTiledSk enc = nullptr;
   static std::once_flag once;
@@ -548,26 +566,24 @@ MM_API int mm_skinny_gemm(const void* x, const void* W, void* y, const void* bia
     MM_CHECK_ARG(r == CUDA_SUCCESS, "mm_skinny_gemm: cuTensorMapEncodeTiled(W) failed (%d)", (int)r);
   }
   {
-    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)m};            // rows >= m of the 8-row box are zero-filled
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)m};            // rows >= m of the box are zero-filled
     cuuint64_t strides[1] = {(cuuint64_t)ldx * 2};
-    cuuint32_t box[2] = {64, 8};
+    cuuint32_t box[2] = {64, (cuuint32_t)(8 * nb)};
     CUresult r = enc(&tx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(x), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MM_CHECK_ARG(r == CUDA_SUCCESS, "mm_skinny_gemm: cuTensorMapEncodeTiled(x) failed (%d)", (int)r);
   }
-  // ring depth (MM_SK2_STAGES / MM_SK2_STAGES32, read once): experiments only
-  static const int nst16 = getenv("MM_SK2_STAGES") ? atoi(getenv("MM_SK2_STAGES")) : 0;
-  static const int nst32 = getenv("MM_SK2_STAGES32") ? atoi(getenv("MM_SK2_STAGES32")) : 0;
-#define MM_SK(R, S) return launch_skinny_tma<R, S>(tw, tx, y, ldy, bias, resid, ldr, m, N, K, epilogue, out_f32, pm, stream)
-  if (rows32) {
-    if (nst32 == 4) MM_SK(32, 4);
-    if (nst32 == 10) MM_SK(32, 10);
-    MM_SK(32, 5);
+  // Ring depths: as deep as keeps two CTAs per SM (profiles/r02_decode_skinny_ring_sweep.txt: deeper rings bought nothing);
+  // 32 sequences x 32-row slabs: 32 KB stages, one CTA per SM.
+#define MM_SK(R, S, B) return launch_skinny_tma<R, S, B>(tw, tx, y, ldy, bias, resid, ldr, m, N, K, epilogue, out_f32, pm, stream)
+  if (nb == 4) MM_SK(32, 5, 4);
+  if (nb == 2) {
+    if (rows32) MM_SK(32, 4, 2);
+    MM_SK(16, 6, 2);
   }
-  if (nst16 == 5) MM_SK(16, 5);
-  if (nst16 == 6) MM_SK(16, 6);
-  MM_SK(16, 8);
+  if (rows32) MM_SK(32, 5, 1);
+  MM_SK(16, 8, 1);
 #undef MM_SK
 }
 

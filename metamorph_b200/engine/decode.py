@@ -29,7 +29,7 @@ class DecodeEngine:
                  end_image_token_id: int = IMAGE_END_TOKEN_ID, eos_token_id=EOS_TOKEN_IDS,
                  forced_tokens: Optional[torch.Tensor] = None, poll_every: int = 16,
                  max_steps: Optional[int] = None):
-        """inputs_embeds [B, P, H] (right-padded to P; prompt_lens[b] valid rows). B <= 8.
+        """inputs_embeds [B, P, H] (right-padded to P; prompt_lens[b] valid rows). B <= 32.
         Returns (ids list per sequence (int32 tensors), image_embeds list per sequence [n, C])."""
         m = self.m
         model = m.get_model()
@@ -37,7 +37,7 @@ class DecodeEngine:
         d = stack.dims
         dev = inputs_embeds.device
         B, P, H = inputs_embeds.shape
-        assert B <= 8, "decode batch is limited to 8 sequences per step (skinny GEMM tile)"
+        assert B <= 32, "decode batch is limited to 32 sequences per step (skinny GEMM: at most four n8 batch tiles)"
         Hq, Hkv, dh = d.n_heads, d.n_kv_heads, d.head_dim
         L = len(model.layers)
         ntok = m.get_vision_tower().image_token_len if m.get_vision_tower() is not None else 0

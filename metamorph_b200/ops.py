@@ -417,7 +417,7 @@ SK_STORE, SK_BIAS, SK_RESID, SK_BIAS_GELU, SK_SWIGLU = range(5)
 
 
 def skinny_gemm(x, w, *, bias=None, resid=None, epilogue=SK_STORE, out=None, out_dtype=torch.bfloat16):
-    """y[m<=8, N] = x[m, K] w[N, K]^T — HBM-bound weight streaming for the decode step."""
+    """y[m<=32, N] = x[m, K] w[N, K]^T — HBM-bound weight streaming for the decode step (the batch is 1, 2 or 4 n8 MMA tiles)."""
     require_cuda(x, w, bias, resid, out)
     m, K = x.shape
     N = w.shape[0]

@@ -44,7 +44,7 @@ def test_bad_arguments_fail_loudly_without_gpu():
         call("mm_rmsnorm_fwd", c_void_p(0), c_void_p(0), c_void_p(0), ll(4), ll(7), c_float(1e-5), c_void_p(0))
     with pytest.raises(MetaMorphB200Error, match="batch"):
         call("mm_skinny_gemm", c_void_p(0), c_void_p(0), c_void_p(0), c_void_p(0), c_void_p(0), ll(64), ll(64),
-             ll(64), ll(0), c_int(9), c_int(64), c_int(64), c_int(0), c_int(0), c_void_p(0))
+             ll(64), ll(0), c_int(33), c_int(64), c_int(64), c_int(0), c_int(0), c_void_p(0))
 
 
 def test_product_never_imports_oracle():

@@ -16,7 +16,7 @@ def _close(a, b, rel, what):
     assert err <= rel * scale, f"{what}: max_err={err:.5f} scale={scale:.4f}"
 
 
-@pytest.mark.parametrize("m", [1, 5, 8])
+@pytest.mark.parametrize("m", [1, 5, 8, 12, 16, 27, 32])
 def test_skinny_gemm(cuda_device, m):
     from metamorph_b200 import ops
     from metamorph_b200.engine.packing import interleave_gate_up
@@ -38,6 +38,10 @@ def test_skinny_gemm(cuda_device, m):
     wu = (torch.randn(512, K, device=cuda_device) * 0.03).bfloat16()
     act = ops.skinny_gemm(x, interleave_gate_up(wg, wu), epilogue=ops.SK_SWIGLU)
     _close(act, F.silu(x.float() @ wg.float().t()) * (x.float() @ wu.float().t()), 1e-2, "swiglu")
+    if m > 8:
+        # more sequences = more n8 tiles of the same MMA: a sequence's result does not depend on who shares the step
+        assert torch.equal(ops.skinny_gemm(x, w)[3:7], ops.skinny_gemm(x[3:7].contiguous(), w))
+        assert torch.equal(act[m - 2:], ops.skinny_gemm(x[m - 2:].contiguous(), interleave_gate_up(wg, wu), epilogue=ops.SK_SWIGLU))
 
 
 @pytest.mark.parametrize("splits", [1, 3, 5])
@@ -85,16 +89,18 @@ def test_argmax_two_stage(cuda_device):
     assert int(ops.argmax_rows(buf, V)[3]) == 77
 
 
-def test_batched_decode_matches_single_sequence_runs(cuda_device):
-    """Batch-8 decode (per-sequence device state machines, ragged prompts) must reproduce each sequence decoded
-    alone (teacher-forced schedule so that bf16 argmax ties cannot make the runs diverge)."""
+@pytest.mark.parametrize("B", [4, 20])
+def test_batched_decode_matches_single_sequence_runs(cuda_device, B):
+    """Batched decode (per-sequence device state machines, ragged prompts; 20 sequences = three n8 batch tiles of the
+    weight-streaming GEMM) must reproduce each sequence decoded alone (teacher-forced schedule so that bf16 argmax ties
+    cannot make the runs diverge)."""
     from oracle.weights import TINY, make_weights
     from tests.helpers import build_product_model
     model = build_product_model(TINY, make_weights(TINY), num_image_tokens=4)
     model.eval()
     g = torch.Generator().manual_seed(5)
-    B, P, steps = 4, 10, 14
-    lens = torch.tensor([10, 7, 9, 4], dtype=torch.int32)
+    P, steps = 10, 14
+    lens = torch.cat([torch.tensor([10, 7, 9, 4]), torch.randint(3, P + 1, (B - 4,), generator=g)]).to(torch.int32)
     prompts = torch.randint(0, 128000, (B, P), generator=g)
     forced = torch.randint(0, 128000, (B, steps + 2), generator=g).to(torch.int32)
     forced[0, 2] = 128256; forced[0, 9] = 128257          # image in sequence 0
