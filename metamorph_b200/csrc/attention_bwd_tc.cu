@@ -54,13 +54,6 @@ struct BwdTcParams {
   float scale;
 };
 
-__device__ __forceinline__ void bulk_load(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_dst),
-               "l"(gsrc), "r"(bytes), "r"(bar)
-               : "memory");
-}
-
 __device__ __forceinline__ void store_bf16x32(bf16* dst, const uint32_t (&a)[32]) {
 #pragma unroll
   for (int t = 0; t < 32; t += 8) {
@@ -320,7 +313,7 @@ flash_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 __global__ void __launch_bounds__(BW_THREADS, 1)
 flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                      const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
-                     BwdTcParams p) {
+                     const __grid_constant__ CUtensorMap tmap_stat, BwdTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // grid = (Hkv*B, key tiles): CTAs are dispatched x-fastest, so ALL (head, batch) instances of the heaviest key tile
@@ -399,11 +392,9 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       // directly (it is also implied by ds_full -> MMA thread -> commit on `empty`, a chain racecheck cannot follow).
       mbar_wait(buf ? stat_empty1 : stat_empty0, (uint32_t)((use & 1) ^ 1));
       mbar_arrive_expect_tx(full, 2 * BW_TILE + 1024);
-      {
-        const long long off = ((long long)b * p.Hq + hq) * p.Tp + q0;
-        bulk_load(uStat + buf * 1024, p.lse2 + off, 512, full);
-        bulk_load(uStat + buf * 1024 + 512, p.delta + off, 512, full);
-      }
+      // statistics rows of the workspace: [lse2 rows of all (b, head) | delta rows of all (b, head)], 128 values each
+      tma_load_2d(uStat + buf * 1024, &tmap_stat, full, q0, b * p.Hq + hq);
+      tma_load_2d(uStat + buf * 1024 + 512, &tmap_stat, full, q0, (p.B + b) * p.Hq + hq);
       tma_load_2d(sQ[buf], &tmap_q, full, hq * 128, tok0 + q0);
       tma_load_2d(sQ[buf] + 16384, &tmap_q, full, hq * 128 + 64, tok0 + q0);
       tma_load_2d(sdO[buf], &tmap_do, full, hq * 128, tok0 + q0);
@@ -601,8 +592,10 @@ int launch_bwd_tc(const void* q, const void* k, const void* v, const void* o, co
                "mm_attn_bwd_tc: 16-byte alignment required");
   const int Tp = (T + 127) / 128 * 128;
   const long long stat_bytes = ((long long)B * Hq * Tp * 4 + 255) / 256 * 256;
-  CUtensorMap tq, tk, tv, tdo, to;
+  CUtensorMap tq, tk, tv, tdo, to, tstat;
   int rc;
+  MM_CHECK_ARG(stat_bytes == (long long)B * Hq * Tp * 4, "mm_attn_bwd_tc: statistics rows must be contiguous");
+  if ((rc = mm_attn_make_tmap_stats(&tstat, reinterpret_cast<const float*>(workspace), Tp, 2LL * B * Hq))) return rc;
   if ((rc = mm_attn_make_tmap_rows(&tq, q, (long long)Hq * 128, total_rows, ldq))) return rc;
   if ((rc = mm_attn_make_tmap_rows(&tk, k, (long long)Hkv * 128, total_rows, ldk))) return rc;
   if ((rc = mm_attn_make_tmap_rows(&tv, v, (long long)Hkv * 128, total_rows, ldv))) return rc;
@@ -629,7 +622,7 @@ int launch_bwd_tc(const void* q, const void* k, const void* v, const void* o, co
   const dim3 grid_k = work_k ? dim3(n_work_k, Hkv, 1) : dim3(Hkv * B, n_tiles, 1);
   flash_bwd_dq_kernel<<<grid_q, BW_THREADS, BW_SMEM, stream>>>(tq, tk, tv, tdo, to, p);
   MM_CHECK_LAUNCH();
-  flash_bwd_dkv_kernel<<<grid_k, BW_THREADS, BW_SMEM, stream>>>(tq, tk, tv, tdo, p);
+  flash_bwd_dkv_kernel<<<grid_k, BW_THREADS, BW_SMEM, stream>>>(tq, tk, tv, tdo, tstat, p);
   MM_CHECK_LAUNCH();
   return MM_OK;
 }

@@ -257,7 +257,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 
 }  // namespace
 
-int mm_attn_make_tmap_rows(CUtensorMap* tm, const void* base, long long width, long long rows, long long ld) {
+static PFN_encodeTiled tmap_encoder() {
   static PFN_encodeTiled enc = nullptr;
   static std::once_flag once;
   std::call_once(once, [] {
@@ -267,10 +267,31 @@ int mm_attn_make_tmap_rows(CUtensorMap* tm, const void* base, long long width, l
         q == cudaDriverEntryPointSuccess)
       enc = reinterpret_cast<PFN_encodeTiled>(fn);
   });
-  if (!enc) {
-    mm_set_error("cuTensorMapEncodeTiled unavailable");
+  if (!enc) mm_set_error("cuTensorMapEncodeTiled unavailable");
+  return enc;
+}
+
+// fp32 statistics rows ([rows, width] contiguous, width % 128 == 0): box = 128 consecutive values of one row, no swizzle.
+int mm_attn_make_tmap_stats(CUtensorMap* tm, const float* base, long long width, long long rows) {
+  PFN_encodeTiled enc = tmap_encoder();
+  if (!enc) return MM_ERR_CUDA;
+  cuuint64_t dims[2] = {(cuuint64_t)width, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)width * 4};
+  cuuint32_t box[2] = {128, 1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    mm_set_error("cuTensorMapEncodeTiled failed (%d) for the attention statistics rows", (int)r);
     return MM_ERR_CUDA;
   }
+  return MM_OK;
+}
+
+int mm_attn_make_tmap_rows(CUtensorMap* tm, const void* base, long long width, long long rows, long long ld) {
+  PFN_encodeTiled enc = tmap_encoder();
+  if (!enc) return MM_ERR_CUDA;
   cuuint64_t dims[2] = {(cuuint64_t)width, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
   cuuint32_t box[2] = {64, 128};

@@ -79,3 +79,5 @@ __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile, int k16) {
 
 // One tensor map per operand: rows = tokens, box = [128 rows x 64 bf16] (128-byte swizzle). Defined in attention_tc.cu.
 int mm_attn_make_tmap_rows(CUtensorMap* tm, const void* base, long long width, long long rows, long long ld);
+// fp32 statistics rows [rows, width] (lse*log2e and delta of the backward): box = 128 values of one row.
+int mm_attn_make_tmap_stats(CUtensorMap* tm, const float* base, long long width, long long rows);

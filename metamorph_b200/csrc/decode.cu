@@ -162,17 +162,19 @@ skinny_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
   __syncthreads();
   if (pdl & 8) griddep_launch();
   if (epi == SK_SWIGLU) {
-    if (ROWS == 32) {
-      for (int idx = threadIdx.x; idx < 16 * MB; idx += SK2_THREADS) {
+    if (ROWS >= 32) {
+      // rows of the slab: [16 gate | 16 up] per group of 32 (engine/packing.py interleave_gate_up)
+      for (int idx = threadIdx.x; idx < (ROWS / 2) * MB; idx += SK2_THREADS) {
         const int r = idx / MB, b = idx % MB;
+        const int gr = (r >> 4) * 32 + (r & 15);
         float gsum = 0.f, usum = 0.f;
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
-          gsum += red[(w * ROWS + r) * MB + b];
-          usum += red[(w * ROWS + r + 16) * MB + b];
+          gsum += red[(w * ROWS + gr) * MB + b];
+          usum += red[(w * ROWS + gr + 16) * MB + b];
         }
         const int col = (n0 >> 1) + r;
-        if (b < m && n0 + r < N)
+        if (b < m && n0 + gr < N)
           reinterpret_cast<bf16*>(y)[(long long)b * ldy + col] = __float2bfloat16(silu(gsum) * usum);
       }
     }
@@ -543,6 +545,9 @@ MM_API int mm_skinny_gemm(const void* x, const void* W, void* y, const void* bia
   // (lm_head: fewer, longer-lived CTAs) and for 32 sequences (each CTA re-reads the whole activation block from L2: the
   // taller slab halves that traffic); 16-row slabs otherwise
   const bool rows32 = (epilogue == SK_SWIGLU) || (N >= 32 * 4 * mm_num_sms()) || nb == 4;
+  // 32 sequences, wide outputs (gate/up, lm_head): 64-row slabs halve the L2 -> SM activation traffic again, which at this
+  // batch equals the weight stream and caps the kernel (measured 4.1 TB/s of weights + as much of x with 32-row slabs)
+  const bool rows64 = nb == 4 && N >= 64 * 2 * mm_num_sms() && (epilogue != SK_SWIGLU || N % 64 == 0);
   if (epilogue == SK_SWIGLU) MM_CHECK_ARG(N % 32 == 0 && !out_f32, "mm_skinny_gemm: SWIGLU needs N%%32==0");
   static PFN_encodeTiledSk enc = nullptr;
   static std::once_flag once;
@@ -559,7 +564,7 @@ MM_API int mm_skinny_gemm(const void* x, const void* W, void* y, const void* bia
   {
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
     cuuint64_t strides[1] = {(cuuint64_t)ldw * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)(rows32 ? 32 : 16)};
+    cuuint32_t box[2] = {64, (cuuint32_t)(rows64 ? 64 : (rows32 ? 32 : 16))};
     CUresult r = enc(&tw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(W), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -575,8 +580,9 @@ MM_API int mm_skinny_gemm(const void* x, const void* W, void* y, const void* bia
     MM_CHECK_ARG(r == CUDA_SUCCESS, "mm_skinny_gemm: cuTensorMapEncodeTiled(x) failed (%d)", (int)r);
   }
   // Ring depths: as deep as keeps two CTAs per SM (profiles/r02_decode_skinny_ring_sweep.txt: deeper rings bought nothing);
-  // 32 sequences x 32-row slabs: 32 KB stages, one CTA per SM.
+  // 32 sequences: 32 KB (32-row slabs) or 48 KB (64-row slabs) stages, one CTA per SM.
 #define MM_SK(R, S, B) return launch_skinny_tma<R, S, B>(tw, tx, y, ldy, bias, resid, ldr, m, N, K, epilogue, out_f32, pm, stream)
+  if (rows64) MM_SK(64, 4, 4);
   if (nb == 4) MM_SK(32, 5, 4);
   if (nb == 2) {
     if (rows32) MM_SK(32, 4, 2);

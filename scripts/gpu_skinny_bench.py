@@ -29,13 +29,14 @@ def bench(N, K, epi=ops.SK_STORE, copies=12, iters=5, m=8):
     e1.record()
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / (iters * copies)
-    print(f"skinny N={N:6d} K={K:6d} epi={epi}: {us:7.1f} us  {N*K*2/us/1e3:7.1f} GB/s", flush=True)
+    print(f"skinny m={m:2d} N={N:6d} K={K:6d} epi={epi}: {us:7.1f} us  {N*K*2/us/1e3:7.1f} GB/s", flush=True)
 
 
-bench(6144, 4096)
-bench(4096, 4096, ops.SK_RESID)
-bench(28672, 4096, ops.SK_SWIGLU)
-bench(4096, 14336, ops.SK_RESID)
-bench(128258, 4096, copies=3)
+for m in ([8, 16, 32] if "--batches" in sys.argv else [8]):
+    bench(6144, 4096, m=m)
+    bench(4096, 4096, ops.SK_RESID, m=m)
+    bench(28672, 4096, ops.SK_SWIGLU, m=m)
+    bench(4096, 14336, ops.SK_RESID, m=m)
+    bench(128258, 4096, copies=3, m=m)
 
 import os

@@ -44,6 +44,27 @@ def test_skinny_gemm(cuda_device, m):
         assert torch.equal(act[m - 2:], ops.skinny_gemm(x[m - 2:].contiguous(), interleave_gate_up(wg, wu), epilogue=ops.SK_SWIGLU))
 
 
+def test_skinny_gemm_batch32_wide_outputs(cuda_device):
+    """32 sequences x wide outputs (gate/up, lm_head shapes) take the 64-row weight slabs: ragged N (out-of-bounds rows of
+    the last slab) and the SwiGLU pairing of two [16 gate | 16 up] groups per slab."""
+    from metamorph_b200 import ops
+    from metamorph_b200.engine.packing import interleave_gate_up
+    torch.manual_seed(1)
+    K = 1024
+    x = torch.randn(32, K, device=cuda_device).bfloat16()
+    for N in (19001, 19072):
+        w = (torch.randn(N, K, device=cuda_device) * 0.03).bfloat16()
+        out32 = torch.empty(32, N, device=cuda_device, dtype=torch.float32)
+        ops.skinny_gemm(x, w, out=out32)
+        _close(out32, x.float() @ w.float().t(), 2e-3, f"fp32 out N={N}")
+        assert torch.equal(ops.skinny_gemm(x, w)[9:14], ops.skinny_gemm(x[9:14].contiguous(), w))
+    wg = (torch.randn(9536, K, device=cuda_device) * 0.03).bfloat16()
+    wu = (torch.randn(9536, K, device=cuda_device) * 0.03).bfloat16()
+    act = ops.skinny_gemm(x, interleave_gate_up(wg, wu), epilogue=ops.SK_SWIGLU)
+    _close(act, F.silu(x.float() @ wg.float().t()) * (x.float() @ wu.float().t()), 1e-2, "swiglu 64-row slabs")
+    assert torch.equal(act[:8], ops.skinny_gemm(x[:8].contiguous(), interleave_gate_up(wg, wu), epilogue=ops.SK_SWIGLU))
+
+
 @pytest.mark.parametrize("splits", [1, 3, 5])
 def test_decode_attention_split_context(cuda_device, splits):
     from metamorph_b200 import ops
