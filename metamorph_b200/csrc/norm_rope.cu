@@ -11,41 +11,61 @@ constexpr int kNormThreads = 256;
 constexpr int kMaxVec = 4;  // 8-element vectors per thread => H <= 8192
 
 // ---------------------------------------------------------------------------------- RMSNorm fwd
-__global__ void __launch_bounds__(kNormThreads)
+// Row r + gridDim.x is requested BEFORE the reduction of row r (as in the backward below): every block keeps a second row
+// of HBM reads in flight across its barrier; the weight vector lives in registers (packed). One __syncthreads per row.
+template <int VPT>   // 8-element vectors per thread (H <= 8 * 256 * VPT)
+__global__ void __launch_bounds__(kNormThreads, (VPT <= 2 ? 4 : 1))
 rmsnorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ y,
                    int M, int H, float eps) {
-  __shared__ float red[32];
+  __shared__ float red[2][kNormThreads / 32];
   const int nvec = H >> 3;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int4 wp[VPT];
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int v = threadIdx.x + i * kNormThreads;
+    wp[i] = v < nvec ? *reinterpret_cast<const int4*>(w + v * 8) : make_int4(0, 0, 0, 0);   // weights: never written by a kernel
+  }
   griddep_launch();
   griddep_wait();
-  for (int row = blockIdx.x; row < M; row += gridDim.x) {
-    const bf16* xr = x + (size_t)row * H;
-    float xv[kMaxVec][8];
+  int4 nx[VPT];
+  auto fetch = [&](int row) {
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      const int v = threadIdx.x + i * kNormThreads;
+      nx[i] = (row < M && v < nvec) ? ld_nc_int4(x + (size_t)row * H + v * 8) : make_int4(0, 0, 0, 0);
+    }
+  };
+  fetch(blockIdx.x);
+  int par = 0;
+  for (int row = blockIdx.x; row < M; row += gridDim.x, par ^= 1) {
+    float xv[VPT][8];
     float ss = 0.f;
 #pragma unroll
-    for (int i = 0; i < kMaxVec; ++i) {
-      const int v = threadIdx.x + i * kNormThreads;
-      if (v < nvec) {
-        const int4 raw = *reinterpret_cast<const int4*>(xr + v * 8);
-        const uint32_t u[4] = {(uint32_t)raw.x, (uint32_t)raw.y, (uint32_t)raw.z, (uint32_t)raw.w};
+    for (int i = 0; i < VPT; ++i) {
+      const uint32_t u[4] = {(uint32_t)nx[i].x, (uint32_t)nx[i].y, (uint32_t)nx[i].z, (uint32_t)nx[i].w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = unpack_bf16x2(u[j]);
-          xv[i][2 * j] = f.x;
-          xv[i][2 * j + 1] = f.y;
-          ss += f.x * f.x + f.y * f.y;
-        }
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2(u[j]);
+        xv[i][2 * j] = f.x;
+        xv[i][2 * j + 1] = f.y;
+        ss += f.x * f.x + f.y * f.y;
       }
     }
-    ss = block_sum(ss, red);
-    const float rstd = rsqrtf(ss / (float)H + eps);
+    fetch(row + gridDim.x);                  // in flight across the reduction below
+    ss = warp_sum(ss);
+    if (lane == 0) red[par][warp] = ss;
+    __syncthreads();
+    float tss = 0.f;
+#pragma unroll
+    for (int k = 0; k < kNormThreads / 32; ++k) tss += red[par][k];
+    const float rstd = rsqrtf(tss / (float)H + eps);
     bf16* yr = y + (size_t)row * H;
 #pragma unroll
-    for (int i = 0; i < kMaxVec; ++i) {
+    for (int i = 0; i < VPT; ++i) {
       const int v = threadIdx.x + i * kNormThreads;
       if (v < nvec) {
-        const int4 wraw = *reinterpret_cast<const int4*>(w + v * 8);
-        const uint32_t wu[4] = {(uint32_t)wraw.x, (uint32_t)wraw.y, (uint32_t)wraw.z, (uint32_t)wraw.w};
+        const uint32_t wu[4] = {(uint32_t)wp[i].x, (uint32_t)wp[i].y, (uint32_t)wp[i].z, (uint32_t)wp[i].w};
         uint32_t o[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -274,8 +294,16 @@ MM_API int mm_rmsnorm_fwd(const void* x, const void* w, void* y, long long M, lo
                           cudaStream_t stream) {
   MM_CHECK_ARG(M > 0 && H > 0 && H % 8 == 0 && H <= 8 * kNormThreads * kMaxVec,
                "mm_rmsnorm_fwd: need H%%8==0 and H<=%d (H=%lld)", 8 * kNormThreads * kMaxVec, H);
-  MM_CHECK_CUDA(launch_pdl(mm_pdl_mode() & 2, rmsnorm_fwd_kernel, dim3(norm_grid((int)M)), dim3(kNormThreads), 0, stream, (const bf16*)x,
-                           (const bf16*)w, (bf16*)y, (int)M, (int)H, eps));
+  const int vpt = (int)((H / 8 + kNormThreads - 1) / kNormThreads);
+  const int cap = mm_num_sms() * (vpt <= 2 ? 8 : 2);     // resident blocks per SM x 2 (tail balance)
+  const dim3 grid(M < cap ? (int)M : cap);
+#define MM_RMS_FWD(V)                                                                                                \
+  MM_CHECK_CUDA(launch_pdl(mm_pdl_mode() & 2, rmsnorm_fwd_kernel<V>, grid, dim3(kNormThreads), 0, stream, (const bf16*)x, \
+                           (const bf16*)w, (bf16*)y, (int)M, (int)H, eps))
+  if (vpt <= 1) MM_RMS_FWD(1);
+  else if (vpt == 2) MM_RMS_FWD(2);
+  else MM_RMS_FWD(4);
+#undef MM_RMS_FWD
   MM_CHECK_LAUNCH();
   return MM_OK;
 }
