@@ -392,13 +392,14 @@ flash_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       // directly (it is also implied by ds_full -> MMA thread -> commit on `empty`, a chain racecheck cannot follow).
       mbar_wait(buf ? stat_empty1 : stat_empty0, (uint32_t)((use & 1) ^ 1));
       mbar_arrive_expect_tx(full, 2 * BW_TILE + 1024);
-      // statistics rows of the workspace: [lse2 rows of all (b, head) | delta rows of all (b, head)], 128 values each
-      tma_load_2d(uStat + buf * 1024, &tmap_stat, full, q0, b * p.Hq + hq);
-      tma_load_2d(uStat + buf * 1024 + 512, &tmap_stat, full, q0, (p.B + b) * p.Hq + hq);
       tma_load_2d(sQ[buf], &tmap_q, full, hq * 128, tok0 + q0);
       tma_load_2d(sQ[buf] + 16384, &tmap_q, full, hq * 128 + 64, tok0 + q0);
       tma_load_2d(sdO[buf], &tmap_do, full, hq * 128, tok0 + q0);
       tma_load_2d(sdO[buf] + 16384, &tmap_do, full, hq * 128 + 64, tok0 + q0);
+      // statistics rows of the workspace: [lse2 rows of all (b, head) | delta rows of all (b, head)], 128 values each
+      // (after the 64 KB of Q / dO: the first MMA of the iteration needs those, the statistics only its elementwise phase)
+      tma_load_2d(uStat + buf * 1024, &tmap_stat, full, q0, b * p.Hq + hq);
+      tma_load_2d(uStat + buf * 1024 + 512, &tmap_stat, full, q0, (p.B + b) * p.Hq + hq);
     }
   } else if (warp == 1 && lane == 0) {
     // ---------------------------------------------------------------- MMA issuer
