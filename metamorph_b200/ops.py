@@ -322,7 +322,12 @@ def attn_fwd(q, k, v, B, T, Hq, Hkv, head_dim, causal, scale, seqlens=None, out=
     if out is None:
         out = torch.empty((B * T, Hq * head_dim), dtype=torch.bfloat16, device=q.device)
     lse = torch.empty((B, Hq, T), dtype=torch.float32, device=q.device) if need_lse else None
-    use_tc = (head_dim == 128) if tc is None else tc
+    # One kernel on the product path: tcgen05, 128-wide head slots (narrower heads are zero-padded into such slots by their
+    # caller, as SiglipVisionTower does). tc=False selects the mma.sync comparison kernels (tests / microbenchmarks only).
+    use_tc = True if tc is None else tc
+    if use_tc and head_dim != 128:
+        raise ValueError(f"attn_fwd: the tcgen05 attention takes head_dim 128 (got {head_dim}); pad the heads into 128-wide "
+                         "slots or pass tc=False for the mma.sync comparison kernel")
     call("mm_attn_fwd_tc" if use_tc else "mm_attn_fwd", ptr(q), ptr(k), ptr(v), ptr(out), ptr(lse), ptr(seqlens), ll(q.stride(0)),
          ll(k.stride(0)), ll(v.stride(0)), ll(out.stride(0)), c_int(B), c_int(T), c_int(Hq),
          c_int(Hkv), c_int(head_dim), c_int(int(causal)), c_float(scale), stream_ptr())
