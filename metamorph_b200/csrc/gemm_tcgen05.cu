@@ -897,6 +897,10 @@ int env_group_m() {
   static const int v = [] { const char* e = getenv("MM_GEMM_GM"); return e ? atoi(e) : 0; }();
   return v;
 }
+int env_panel_mb() {   // MM_GEMM_PANEL_MB: L2 budget of the A panel of a rasterisation group (2-CTA kernel), default 32
+  static const int v = [] { const char* e = getenv("MM_GEMM_PANEL_MB"); return e ? atoi(e) : 32; }();
+  return v;
+}
 int env_dynamic_tiles() {   // MM_GEMM_DYNAMIC=0 selects the static persistent schedule of the 2-CTA kernel (A/B measurements)
   static const int v = [] { const char* e = getenv("MM_GEMM_DYNAMIC"); return e ? atoi(e) : 1; }();
   return v;
@@ -953,7 +957,7 @@ int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
   int clusters = mm_num_sms() / 2;
   if (clusters > num_tiles || DYN) clusters = num_tiles;     // dynamic: one cluster per tile, the resident ones steal the rest
   // same rule as the 1-CTA launcher with 256-row blocks and 74 concurrent cluster tiles (square wave: 8 x 9)
-  long long gm = (32ll << 20) / ((long long)2 * BM * K * 2);
+  long long gm = ((long long)env_panel_mb() << 20) / ((long long)2 * BM * K * 2);
   if (gm < 8) gm = 8;
   if (gm > 32) gm = 32;
   if (env_group_m() > 0) gm = env_group_m();   // rasterisation experiments (MM_GEMM_GM, read once)
