@@ -157,7 +157,9 @@ int mm_siglip_preprocess(const void* img, int H, int W, int pad_square, int fill
                          const void* coeff_y, int ksize_x, int ksize_y, int out_size, const float* lut, void* tmp,
                          void* out, int out_bf16, cudaStream_t s);
 
-/* KV-cached decode step (replaces the no-cache loop of greedy_decode, metamorph_llama.py:502-597). */
+/* KV-cached decode step (replaces the no-cache loop of greedy_decode, metamorph_llama.py:502-597).
+ * mm_skinny_gemm: y[m, N] = x[m, K] W[N, K]^T for 1 <= m <= 32 sequences (weights streamed once per call);
+ * epilogue 0 store, 1 +bias, 2 +resid, 3 +bias then GELU(erf), 4 SwiGLU over 16-row interleaved gate/up (y is [m, N/2]). */
 int mm_skinny_gemm(const void* x, const void* W, void* y, const void* bias, const void* resid, long long ldx,
                    long long ldw, long long ldy, long long ldr, int m, int N, int K, int epilogue, int out_f32,
                    cudaStream_t s);
