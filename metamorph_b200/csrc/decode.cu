@@ -73,7 +73,7 @@ skinny_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_
       // The activation slice of a stage travels WITH its weights: one transaction, NST stages of look-ahead. (Round 1
       // fetched each lane's x fragments through a private 2-deep cp.async ring: every stage then waited an L2 round trip
       // for fragments requested two stages earlier, which capped a CTA at ~30 GB/s whatever the ring depth —
-      // profiles/r02_decode_skinny_gemm.txt.) The weights of the first NST stages are requested BEFORE waiting for the
+      // profiles/r02_decode_skinny_fit_before.txt.) The weights of the first NST stages are requested BEFORE waiting for the
       // previous kernel (they never change during a step); x, which that kernel produces, follows after the wait.
       const int n_pre = n_kt < NST ? n_kt : NST;
       for (int kt = 0; kt < n_pre; ++kt) {

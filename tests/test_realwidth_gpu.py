@@ -38,7 +38,7 @@ def case(request, cuda_device):
 def _budget(ours, ref32, ref16, floor, what):
     """The bf16 budget of tests/test_model_gpu.py AND a much tighter bound: the reference's eager bf16 run rounds after
     every op (its logits sit ~1.1 away from its own fp32 run at this width), the fused kernels keep fp32 accumulators:
-    measured 0.05-0.06 (profiles/r02_gpu_tests.txt), asserted <= 0.25 x the bf16 reference's own error."""
+    measured 0.05-0.06 (profiles/r02_gpu_tests_final.txt), asserted <= 0.25 x the bf16 reference's own error."""
     err = (ours.float().cpu() - ref32).abs().max().item()
     ref_err = (ref16.float() - ref32).abs().max().item()
     bud = 1.5 * ref_err + floor
