@@ -50,3 +50,22 @@ def test_pack_plan_is_a_relayout(pack_len):
     assert pairs(packed) == pairs(plan)
     assert packed.target_image_idx == plan.target_image_idx
     assert packed.batch * packed.seq_len <= plan.batch * plan.seq_len or pack_len is not None
+
+
+def test_segment_tables_cover_every_tile_once_heaviest_first():
+    """Work lists of the one-launch packed attention (ops.SegmentTables): each (sequence, 128-row tile) appears exactly
+    once in the query list (forward / dQ) and in the key list (dK/dV), ordered by the number of tiles it will visit."""
+    from metamorph_b200.ops import SegmentTables
+    segs = [(0, 300), (300, 1), (301, 128), (429, 1501), (1930, 129)]
+    t = SegmentTables(segs, "cpu")
+    assert t.n_seg == 5 and t.max_len == 1501 and t.total == 300 + 1 + 128 + 1501 + 129
+    assert t.start.tolist() == [a for a, _ in segs] and t.length.tolist() == [n for _, n in segs]
+    want = {(s, j) for s, (_, n) in enumerate(segs) for j in range((n + 127) // 128)}
+    wq = t.work_q.view(-1, 2).tolist()
+    wk = t.work_k.view(-1, 2).tolist()
+    assert t.n_work_q == len(wq) == len(want) and t.n_work_k == len(wk) == len(want)
+    assert {tuple(x) for x in wq} == want and {tuple(x) for x in wk} == want
+    ntile = [(n + 127) // 128 for _, n in segs]
+    cost_q = [j + 1 for s, j in wq]                     # a causal query tile attends to j+1 key tiles
+    cost_k = [ntile[s] - j for s, j in wk]              # a key tile is visited by the query tiles at or after it
+    assert cost_q == sorted(cost_q, reverse=True) and cost_k == sorted(cost_k, reverse=True)
